@@ -1,0 +1,159 @@
+/*
+ * mpxb.h -- C ABI of libmpxb.so: the B200-native (sm_100a) primal-dual iLQR solve of iit-DLSLab/mpx.
+ *
+ * Drop-in boundary.  In the reference the path is the Python callable
+ *     work = partial(optimizers.mpc, cost, dynamics, hessian_approx, limited_memory)
+ *     X, U, V = jax.jit(work)(reference, parameter, W, x0, X_in, U_in, V_in)
+ * (reference mpx/primal_dual_ilqr/primal_dual_ilqr/optimizers.py:603-683; built at
+ * mpx/utils/mpc_wrapper.py:74,244,249 and mpx/utils/mpc_wrapper_srbd.py:68,77; called at
+ * mpc_wrapper.py:150-158,346-354,434-442 and mpc_wrapper_srbd.py:124-132).
+ * A JAX maintainer binds mpxb_mpc_step as an XLA-FFI custom call; this repo's own host
+ * code binds it with ctypes (mpx_b200/_lib.py).
+ *
+ * Conventions
+ *   - every array is float32, row-major C-contiguous, leading axis E = environments ([E, knot, feature]);
+ *   - all pointers are DEVICE pointers owned by the caller (inputs read-only, outputs fully overwritten);
+ *   - calls are asynchronous on `stream`, allocate nothing, never synchronise and can be captured in a CUDA graph;
+ *   - return value: 0 on success, negative MPXB_E* for ARGUMENT errors only.  Numerical failure is reported
+ *     in-band exactly like the reference (NaNs in the outputs, mpc_wrapper.py:96,280) plus status[e] != 0.
+ *   - no global mutable state; a model handle is immutable after creation and may be used from several
+ *     streams of its device concurrently as long as each call has its own workspace.
+ */
+#ifndef MPXB_H_
+#define MPXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPXB_VERSION 1
+
+/* dynamics/cost family == reference function triple (models.py / objectives.py) */
+enum {
+  MPXB_KIND_SRBD = 0,     /* quadruped_srbd_dynamics / _obj / _hessian_gn   (models.py:6-37,   objectives.py:15-75)   */
+  MPXB_KIND_QUAD_WB = 1,  /* quadruped_wb_dynamics / _obj / _hessian_gn     (models.py:39-117, objectives.py:77-202)  */
+  MPXB_KIND_H1_WB = 2,    /* h1_wb_dynamics / _obj / _hessian_gn            (models.py:119-169, objectives.py:204-323) */
+  MPXB_KIND_TALOS_WB = 3  /* talos_wb_dynamics / _obj / _hessian_gn         (models.py:170-217, objectives.py:325-450) */
+};
+
+/* LQ sub-problem solver == the reference's `limited_memory` static argument (optimizers.py:175-180) */
+enum {
+  MPXB_LQ_SEQUENTIAL = 0, /* tvlqr + rollout          (primal_tvlqr.py:103-144, 478-498)  limited_memory=True  */
+  MPXB_LQ_SCAN = 1        /* tvlqr_gpu + rollout_gpu  (primal_tvlqr.py:337-475, 523-549)  limited_memory=False */
+};
+
+enum {
+  MPXB_OK = 0,
+  MPXB_EINVAL = -1,      /* null pointer / bad dimension / unknown kind */
+  MPXB_EUNSUPPORTED = -2,/* (n, m) or tree size outside the compiled kernel set */
+  MPXB_EWORKSPACE = -3,  /* workspace_bytes too small */
+  MPXB_ECUDA = -4        /* a CUDA runtime call failed at model creation (never returned by mpxb_mpc_step) */
+};
+
+#define MPXB_MAX_BODY 32
+#define MPXB_MAX_DOF 32
+#define MPXB_MAX_CONTACT 8
+
+/* Flat model description (host memory).  The Python side fills it from the config module and the MJCF
+ * model table (the reference does the same through mujoco.MjModel.from_xml_path + mjx.put_model,
+ * mpc_wrapper.py:43-47).  Whole-body fields are ignored for MPXB_KIND_SRBD and vice versa. */
+typedef struct mpxb_model_desc {
+  int32_t version;        /* MPXB_VERSION */
+  int32_t kind;           /* MPXB_KIND_* */
+  int32_t n, m, N;        /* state dim, control dim, horizon (config.n, config.m, config.N) */
+  int32_t n_joints;       /* config.n_joints */
+  int32_t n_contact;      /* config.n_contact */
+  int32_t nref, npar, nw; /* columns of reference / parameter, side of W */
+  int32_t swing_tracking; /* the flag bound by partial(quadruped_wb_obj, True) (config_go2.py:67) */
+  float dt;               /* config.dt */
+  /* ---- SRBD (config_srbd.py:60-65) ---- */
+  float mass;
+  float inertia[9];
+  float inertia_inv[9];
+  /* ---- whole body: MuJoCo-named tree arrays, body 0 = world (mpx_b200/mjcf.py) ---- */
+  int32_t nbody, nv;
+  float gravity[3];
+  float baumgarte_alpha;  /* models.py:93 (25) / :146 (5) */
+  float contact_reg;      /* models.py:155 (1e-3) */
+  int32_t body_parentid[MPXB_MAX_BODY];
+  int32_t body_dofadr[MPXB_MAX_BODY];   /* first dof of the body's joint, -1 if none */
+  int32_t body_jnttype[MPXB_MAX_BODY];  /* 0 free, 3 hinge, -1 none (one joint per body) */
+  float body_pos[MPXB_MAX_BODY][3];
+  float body_quat[MPXB_MAX_BODY][4];
+  float body_ipos[MPXB_MAX_BODY][3];
+  float body_iquat[MPXB_MAX_BODY][4];
+  float body_mass[MPXB_MAX_BODY];
+  float body_inertia[MPXB_MAX_BODY][3];
+  float jnt_pos[MPXB_MAX_BODY][3];      /* indexed by body */
+  float jnt_axis[MPXB_MAX_BODY][3];
+  float jnt_qpos0[MPXB_MAX_BODY];       /* hinge reference angle */
+  float dof_armature[MPXB_MAX_DOF];
+  int32_t contact_body[MPXB_MAX_CONTACT]; /* body carrying foot point i, in the model's contact order */
+  float contact_pos[MPXB_MAX_CONTACT][3]; /* foot point in that body's frame (geom_pos) */
+} mpxb_model_desc;
+
+typedef struct mpxb_model mpxb_model; /* opaque; owns its constant device tables */
+
+/* Create / destroy a model on the CURRENT CUDA device.  Replaces the reference's per-wrapper setup
+ * (mpc_wrapper.py:43-74, mpc_wrapper_srbd.py:33-68). */
+int mpxb_model_create(const mpxb_model_desc* desc, mpxb_model** out);
+void mpxb_model_destroy(mpxb_model* model);
+
+/* Bytes of device scratch one mpxb_mpc_step call with E environments needs. */
+size_t mpxb_workspace_bytes(const mpxb_model* model, int E, int lq_mode);
+
+/* One call == `max_iter` SQP iterations of optimizers.mpc for each of E environments (max_iter = 1 is the
+ * reference's real-time iteration).  With max_iter > 1 the loop runs stream-ordered on the device and an
+ * environment stops early once the offline stopping rule of mpc_wrapper.py:463-467 holds
+ * (last_cost - g*g < 1e-3 and sum(c*c) < 1e-5); iters[e] reports the iterations actually taken.
+ *
+ *   reference [E,N+1,nref]  parameter [E,N+1,npar]  W [nw,nw] if w_env_stride == 0 else [E,nw,nw]
+ *   x0 [E,n]  X_in/X [E,N+1,n]  U_in/U [E,N,m]  V_in/V [E,N+1,n]
+ *   alpha_index [E]  index i of the accepted step 2^-i (10 if none, optimizers.py:572)      (may be NULL)
+ *   iters [E], status [E]  (status bit 0: non-finite value in X/U/V)                        (may be NULL)
+ * X/U/V must not alias X_in/U_in/V_in. */
+int mpxb_mpc_step(const mpxb_model* model, void* stream /* cudaStream_t */, int E, int lq_mode, int max_iter,
+                  const float* reference, const float* parameter, const float* W, size_t w_env_stride,
+                  const float* x0, const float* X_in, const float* U_in, const float* V_in,
+                  float* X, float* U, float* V,
+                  int32_t* alpha_index, int32_t* iters, int32_t* status,
+                  void* workspace, size_t workspace_bytes);
+
+/* Read-only views into the workspace of the LAST mpxb_mpc_step call (gains, value function, search
+ * direction, linearisation) for parity tests: name in {"A","B","Q","R","M","q","r","c","K","k","P","p",
+ * "dX","dU","dV","ls_theta","ls_phi","g"}.  Returns a device pointer inside `workspace` or NULL. */
+const float* mpxb_workspace_view(const mpxb_model* model, int E, int lq_mode, void* workspace, const char* name,
+                                 size_t* count);
+
+/* Warm-start shift / NaN guard / command extraction of update_and_extract_helper
+ * (mpc_wrapper.py:79-98, 261-282; mpc_wrapper_srbd.py:135-139), batched over E, stream-ordered.
+ *   X,U,V: solution of this tick; X0,U0,V0: previous warm start (in) -> next warm start (out);
+ *   tau [E,n_joints], q [E,n_joints], dq [E,n_joints] (whole-body kinds; NULL for SRBD). */
+int mpxb_shift_extract(const mpxb_model* model, void* stream, int E, int shift,
+                       const float* X, const float* U, const float* V, const float* x0, const float* u_ref,
+                       float* X0, float* U0, float* V0, float* tau, float* q, float* dq);
+
+/* Standalone LQ sub-problem solve, batched over E: the reference functions tvlqr + rollout + dual_lqr
+ * (lq_mode = MPXB_LQ_SEQUENTIAL; primal_tvlqr.py:103-144, 478-498; dual_tvlqr.py:6-19) or tvlqr_gpu + rollout_gpu +
+ * dual_lqr (MPXB_LQ_SCAN; primal_tvlqr.py:337-475, 523-549) as compute_search_direction calls them
+ * (optimizers.py:175-182).  c is [E,N+1,n]: c[:,0] is the rollout's initial offset (optimizers.py:177 passes c[0]),
+ * c[:,1:] the dynamics offsets.  Outputs K [E,N,m,n], k [E,N,m], P [E,N+1,n,n], p [E,N+1,n], dX, dU, dV and
+ * slope [E] = sum(q*dX) + sum(r*dU).  scan_ws: mpxb_tvlqr_scan_bytes() bytes of device scratch (scan mode only). */
+int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const float* Q, const float* q, const float* R,
+               const float* r, const float* M, const float* A, const float* B, const float* c,
+               float* K, float* k, float* P, float* p, float* dX, float* dU, float* dV, float* slope, void* scan_ws);
+size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m);
+
+/* FP32 FFMA throughput micro-benchmark (roofline denominator).  Returns TFLOP/s measured with
+ * CUDA events on `stream`, or a negative MPXB_E*. */
+double mpxb_fp32_peak_tflops(void* stream, int iters);
+
+const char* mpxb_version_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPXB_H_ */

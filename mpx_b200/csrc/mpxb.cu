@@ -1,0 +1,277 @@
+// mpxb.cu -- C ABI of libmpxb.so (include/mpxb.h): model handles, workspace layout, and the stream-ordered
+// launch sequence of one primal-dual iLQR iteration:
+//   K1 <model>_linearize : evaluate + linearise + quadratise, one warp per knot per env   (optimizers.py:625,150-173)
+//   K2 lq_seq / lq_scan  : Riccati backward pass, rollout, dual update                     (primal_tvlqr.py, dual_tvlqr.py)
+//   K3 <model>_trial     : 11 trial points of the filter line search                       (optimizers.py:518-540)
+//   K4 select_update     : filter decision, iterate update, convergence flag               (optimizers.py:541-578)
+// There is no host synchronisation and no allocation on this path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/mpxb.h"
+#include "lq.cuh"
+#include "sqp.cuh"
+#include "srbd_kernels.cuh"
+#include "wb_kernels.cuh"
+#include "lq_scan.cuh"
+
+using namespace mpxb;
+
+struct mpxb_model {
+  mpxb_model_desc desc;
+  SrbdParams srbd;
+  WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
+  WbModel wb_host;
+  int device;
+};
+
+namespace {
+
+template <int n, int m> cudaError_t launch_lq_seq(const LqArgs& a, cudaStream_t st) {
+  constexpr int NT = 256;
+  auto kern = lq_seq_kernel<n, m, NT>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LqSmemLayout<n, m>::bytes));
+    if (err != cudaSuccess) return err;
+    configured[dev] = true;
+  }
+  kern<<<a.E, NT, LqSmemLayout<n, m>::bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+int dispatch_lq_seq(int n, int m, const LqArgs& a, cudaStream_t st) {
+  cudaError_t err;
+#define MPXB_LQ_CASE(NN, MM) if (n == NN && m == MM) { err = launch_lq_seq<NN, MM>(a, st); return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA; }
+  MPXB_LQ_CASE(13, 12)
+  MPXB_LQ_CASE(61, 12)
+  MPXB_LQ_CASE(75, 19)
+  MPXB_LQ_CASE(81, 46)
+  MPXB_LQ_CASE(2, 1)
+  MPXB_LQ_CASE(4, 1)
+  MPXB_LQ_CASE(8, 2)
+#undef MPXB_LQ_CASE
+  return MPXB_EUNSUPPORTED;
+}
+
+bool lq_supported(int n, int m) {
+  const int s[][2] = {{13, 12}, {61, 12}, {75, 19}, {81, 46}, {2, 1}, {4, 1}, {8, 2}};
+  for (auto& p : s) if (p[0] == n && p[1] == m) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mpxb_version_string(void) { return "mpxb 0.1 (sm_100a)"; }
+
+int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
+  if (!d || !out) return MPXB_EINVAL;
+  if (d->version != MPXB_VERSION) return MPXB_EINVAL;
+  if (d->kind < MPXB_KIND_SRBD || d->kind > MPXB_KIND_TALOS_WB) return MPXB_EINVAL;
+  if (d->n <= 0 || d->m <= 0 || d->N <= 0) return MPXB_EINVAL;
+  if (!lq_supported(d->n, d->m)) return MPXB_EUNSUPPORTED;
+  mpxb_model* mdl = new (std::nothrow) mpxb_model();
+  if (!mdl) return MPXB_EINVAL;
+  mdl->desc = *d;
+  mdl->wb_dev = nullptr;
+  cudaGetDevice(&mdl->device);
+  if (d->kind == MPXB_KIND_SRBD) {
+    if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
+      delete mdl;
+      return MPXB_EINVAL;
+    }
+    mdl->srbd.mass = d->mass;
+    mdl->srbd.dt = d->dt;
+    memcpy(mdl->srbd.inertia, d->inertia, sizeof(float) * 9);
+    memcpy(mdl->srbd.inertia_inv, d->inertia_inv, sizeof(float) * 9);
+  } else {
+    int rc = wb_build_model(*d, &mdl->wb_host);
+    if (rc != MPXB_OK) { delete mdl; return rc; }
+    if (cudaMalloc(&mdl->wb_dev, sizeof(WbModel)) != cudaSuccess) { delete mdl; return MPXB_ECUDA; }
+    if (cudaMemcpy(mdl->wb_dev, &mdl->wb_host, sizeof(WbModel), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(mdl->wb_dev);
+      delete mdl;
+      return MPXB_ECUDA;
+    }
+  }
+  *out = mdl;
+  return MPXB_OK;
+}
+
+void mpxb_model_destroy(mpxb_model* m) {
+  if (!m) return;
+  if (m->wb_dev) cudaFree(m->wb_dev);
+  delete m;
+}
+
+static WsLayout layout_of(const mpxb_model* mdl, int E, int lq_mode) {
+  const mpxb_model_desc& d = mdl->desc;
+  size_t scan = (lq_mode == MPXB_LQ_SCAN) ? lq_scan_floats(E, d.N, d.n, d.m) : 0;
+  return make_layout(E, d.N, d.n, d.m, scan);
+}
+
+size_t mpxb_workspace_bytes(const mpxb_model* mdl, int E, int lq_mode) {
+  if (!mdl || E <= 0) return 0;
+  return layout_of(mdl, E, lq_mode).total * sizeof(float);
+}
+
+int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int max_iter, const float* reference,
+                  const float* parameter, const float* W, size_t w_env_stride, const float* x0, const float* X_in,
+                  const float* U_in, const float* V_in, float* X, float* U, float* V, int32_t* alpha_index,
+                  int32_t* iters, int32_t* status, void* workspace, size_t workspace_bytes) {
+  if (!mdl || !reference || !parameter || !W || !x0 || !X_in || !U_in || !V_in || !X || !U || !V || !workspace)
+    return MPXB_EINVAL;
+  if (E <= 0 || max_iter <= 0) return MPXB_EINVAL;
+  if (lq_mode != MPXB_LQ_SEQUENTIAL && lq_mode != MPXB_LQ_SCAN) return MPXB_EINVAL;
+  if (X == X_in || U == U_in || V == V_in) return MPXB_EINVAL;
+  const mpxb_model_desc& d = mdl->desc;
+  const WsLayout L = layout_of(mdl, E, lq_mode);
+  if (workspace_bytes < L.total * sizeof(float)) return MPXB_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  const int N = d.N, n = d.n, m = d.m;
+  int32_t* done = (max_iter > 1) ? reinterpret_cast<int32_t*>(ws + L.done) : nullptr;
+  if (done) cudaMemsetAsync(done, 0, sizeof(int32_t) * E, st);
+
+  // ping-pong so that the last iteration writes the caller's X/U/V
+  const float *Xc = X_in, *Uc = U_in, *Vc = V_in;
+  for (int it = 0; it < max_iter; ++it) {
+    const bool to_user = ((max_iter - 1 - it) % 2) == 0;
+    float* Xn = to_user ? X : ws + L.Xt;
+    float* Un = to_user ? U : ws + L.Ut;
+    float* Vn = to_user ? V : ws + L.Vt;
+    ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
+    LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost};
+    TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi};
+    // K1
+    if (d.kind == MPXB_KIND_SRBD) {
+      const int wpb = 4;
+      const int blocks = (E * (N + 1) + wpb - 1) / wpb;
+      srbd_linearize_kernel<<<blocks, wpb * 32, 0, st>>>(mdl->srbd, io, lo);
+    } else {
+      int rc = wb_launch_linearize(mdl->wb_host, mdl->wb_dev, io, lo, st);
+      if (rc != MPXB_OK) return rc;
+    }
+    // K2
+    LqArgs la{E, N, ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c,
+              ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done};
+    int rc = (lq_mode == MPXB_LQ_SEQUENTIAL) ? dispatch_lq_seq(n, m, la, st)
+                                             : dispatch_lq_scan(n, m, la, ws + L.scan, st);
+    if (rc != MPXB_OK) return rc;
+    // K3
+    if (d.kind == MPXB_KIND_SRBD) {
+      const int wpb = 4;
+      const int blocks = (E * NALPHA + wpb - 1) / wpb;
+      srbd_trial_kernel<<<blocks, wpb * 32, 0, st>>>(mdl->srbd, io, to);
+    } else {
+      rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, io, to, st);
+      if (rc != MPXB_OK) return rc;
+    }
+    // K4
+    SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.cost, ws + L.c, ws + L.ls_theta,
+                  ws + L.ls_phi, ws + L.slope, Xn, Un, Vn, ws + L.g, ws + L.last_cost, done, alpha_index, iters,
+                  status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0};
+    select_update_kernel<<<E, 128, 0, st>>>(sa);
+    Xc = Xn; Uc = Un; Vc = Vn;
+  }
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+const float* mpxb_workspace_view(const mpxb_model* mdl, int E, int lq_mode, void* workspace, const char* name,
+                                 size_t* count) {
+  if (!mdl || !workspace || !name) return nullptr;
+  const mpxb_model_desc& d = mdl->desc;
+  const WsLayout L = layout_of(mdl, E, lq_mode);
+  const size_t e = size_t(E), N = d.N, n = d.n, m = d.m;
+  struct Ent { const char* nm; size_t off, cnt; } ents[] = {
+      {"A", L.A, e * N * n * n}, {"B", L.B, e * N * n * m}, {"Q", L.Q, e * (N + 1) * n * n},
+      {"R", L.R, e * N * m * m}, {"M", L.M, e * N * n * m}, {"q", L.q, e * (N + 1) * n}, {"r", L.r, e * N * m},
+      {"c", L.c, e * (N + 1) * n}, {"K", L.K, e * N * m * n}, {"k", L.k, e * N * m}, {"P", L.P, e * (N + 1) * n * n},
+      {"p", L.p, e * (N + 1) * n}, {"dX", L.dX, e * (N + 1) * n}, {"dU", L.dU, e * N * m},
+      {"dV", L.dV, e * (N + 1) * n}, {"ls_theta", L.ls_theta, e * NALPHA}, {"ls_phi", L.ls_phi, e * NALPHA},
+      {"g", L.g, e}, {"cost", L.cost, e * (N + 1)}, {"slope", L.slope, e}};
+  for (auto& en : ents)
+    if (strcmp(en.nm, name) == 0) {
+      if (count) *count = en.cnt;
+      return static_cast<float*>(workspace) + en.off;
+    }
+  return nullptr;
+}
+
+int mpxb_shift_extract(const mpxb_model* mdl, void* stream, int E, int shift, const float* X, const float* U,
+                       const float* V, const float* x0, const float* u_ref, float* X0, float* U0, float* V0,
+                       float* tau, float* q, float* dq) {
+  if (!mdl || !X || !U || !V || !x0 || !u_ref || !X0 || !U0 || !V0 || E <= 0 || shift < 0) return MPXB_EINVAL;
+  const mpxb_model_desc& d = mdl->desc;
+  const int wb = d.kind != MPXB_KIND_SRBD;
+  shift_extract_kernel<<<E, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, d.N, d.n, d.m, d.n_joints, shift, wb, X, U,
+                                                                         V, x0, u_ref, X0, U0, V0, tau, q, dq);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+// Standalone LQ solve (tvlqr + rollout + dual_lqr, or the scan forms): the reference functions a13-a16 of SURVEY 8a.
+int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const float* Q, const float* q, const float* R,
+               const float* r, const float* M, const float* A, const float* B, const float* c /*[E,N+1,n]: c[0]=x0 offset*/,
+               float* K, float* k, float* P, float* p, float* dX, float* dU, float* dV, float* slope, void* scan_ws) {
+  if (!Q || !q || !R || !r || !M || !A || !B || !c || !K || !k || !P || !p || !dX || !dU || !dV || !slope) return MPXB_EINVAL;
+  LqArgs la{E, N, A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, slope, nullptr};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (lq_mode == MPXB_LQ_SEQUENTIAL) return dispatch_lq_seq(n, m, la, st);
+  if (!scan_ws) return MPXB_EINVAL;
+  return dispatch_lq_scan(n, m, la, static_cast<float*>(scan_ws), st);
+}
+
+size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m) { return lq_scan_floats(E, N, n, m) * sizeof(float); }
+
+__global__ void fp32_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+        a7 = a0 + 7.f;
+  const float b = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double mpxb_fp32_peak_tflops(void* stream, int iters) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256;
+  float* out = nullptr;
+  if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return MPXB_ECUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  fp32_peak_kernel<<<blocks, threads, 0, st>>>(out, 64);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    fp32_peak_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8 * 16 * double(iters) * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+}  // extern "C"

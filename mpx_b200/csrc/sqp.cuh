@@ -1,0 +1,195 @@
+// sqp.cuh -- workspace layout and the model-independent kernels of one SQP iteration:
+// filter line-search decision + iterate update + convergence bookkeeping (optimizers.py:468-578,
+// mpc_wrapper.py:456-467) and the warm-start shift (mpc_wrapper.py:79-98).
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace mpxb {
+
+constexpr int NALPHA = 11;  // alpha_values = exp2(-arange(11))  (optimizers.py:518)
+
+// Offsets (in floats) of each per-batch array inside the caller's workspace.
+struct WsLayout {
+  size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
+      done, scan, total;
+};
+
+inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
+
+inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
+  WsLayout L;
+  size_t o = 0;
+  auto take = [&](size_t cnt) { size_t r = o; o = align64(o + cnt); return r; };
+  const size_t e = size_t(E);
+  L.A = take(e * N * n * n);
+  L.B = take(e * N * n * m);
+  L.Q = take(e * (N + 1) * n * n);
+  L.R = take(e * N * m * m);
+  L.M = take(e * N * n * m);
+  L.q = take(e * (N + 1) * n);
+  L.r = take(e * N * m);
+  L.c = take(e * (N + 1) * n);
+  L.K = take(e * N * m * n);
+  L.k = take(e * N * m);
+  L.P = take(e * (N + 1) * n * n);
+  L.p = take(e * (N + 1) * n);
+  L.dX = take(e * (N + 1) * n);
+  L.dU = take(e * N * m);
+  L.dV = take(e * (N + 1) * n);
+  L.cost = take(e * (N + 1));
+  L.ls_theta = take(e * NALPHA);
+  L.ls_phi = take(e * NALPHA);
+  L.slope = take(e);
+  L.g = take(e);
+  L.Xt = take(e * (N + 1) * n);  // ping-pong iterate for max_iter > 1
+  L.Ut = take(e * N * m);
+  L.Vt = take(e * (N + 1) * n);
+  L.last_cost = take(e);
+  L.done = take(e);  // int32
+  L.scan = take(scan_floats);
+  L.total = o;
+  return L;
+}
+
+struct SelectArgs {
+  int E, N, n, m;
+  const float *X_in, *U_in, *V_in, *dX, *dU, *dV;
+  const float *cost, *c, *ls_theta, *ls_phi, *slope;
+  float *X, *U, *V;
+  float* g_out;
+  float* last_cost;      // per env, offline stopping rule state (may be null)
+  int32_t* done;         // per env (may be null)
+  int32_t *alpha_index, *iters, *status;  // may be null
+  int check_convergence;  // 1 when max_iter > 1
+  int first_iter;
+};
+
+// One CTA per env: theta_k, phi_k, filter tests for the 11 trial points, chosen alpha, iterate update.
+__global__ void select_update_kernel(SelectArgs a) {
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int N = a.N, n = a.n, m = a.m;
+  const size_t nx = size_t(N + 1) * n, nu = size_t(N) * m;
+  const float* Xi = a.X_in + e * nx;
+  const float* Ui = a.U_in + e * nu;
+  const float* Vi = a.V_in + e * nx;
+  float* Xo = a.X + e * nx;
+  float* Uo = a.U + e * nu;
+  float* Vo = a.V + e * nx;
+  if (a.done && a.done[e]) {  // converged earlier: carry the iterate through the ping-pong buffers
+    for (size_t i = tid; i < nx; i += blockDim.x) { Xo[i] = Xi[i]; Vo[i] = Vi[i]; }
+    for (size_t i = tid; i < nu; i += blockDim.x) Uo[i] = Ui[i];
+    return;
+  }
+  __shared__ float s_red[2][32];
+  __shared__ int s_idx;
+  __shared__ float s_alpha;
+  // theta_k = sum c^2 , phi_k = sum_t cost_t  (fixed-order block reduction: deterministic)
+  float th = 0.f, ph = 0.f;
+  const float* c = a.c + e * nx;
+  for (size_t i = tid; i < nx; i += blockDim.x) th = fmaf(c[i], c[i], th);
+  for (int t = tid; t <= N; t += blockDim.x) ph += a.cost[size_t(e) * (N + 1) + t];
+  for (int o = 16; o > 0; o >>= 1) {
+    th += __shfl_xor_sync(0xffffffffu, th, o);
+    ph += __shfl_xor_sync(0xffffffffu, ph, o);
+  }
+  if ((tid & 31) == 0) { s_red[0][tid >> 5] = th; s_red[1][tid >> 5] = ph; }
+  __syncthreads();
+  if (tid == 0) {
+    float theta_k = 0.f, phi_k = 0.f;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) { theta_k += s_red[0][w]; phi_k += s_red[1][w]; }
+    const float slope = a.slope[e];
+    const float theta_max = 1e-2f, theta_min = 1e-6f, eta = 1e-4f, gamma_phi = 1e-6f, gamma_theta = 1e-6f;
+    int best = NALPHA - 1;  // index -1 of the 11 trials when none is accepted (optimizers.py:572)
+    for (int i = NALPHA - 1; i >= 0; --i) {
+      const float alpha = exp2f(-float(i));
+      const float theta_new = a.ls_theta[e * NALPHA + i];
+      const float phi_new = a.ls_phi[e * NALPHA + i];
+      const bool cond1 = theta_new > theta_max;
+      const bool case1 = cond1 && (theta_new < (1.f - gamma_theta) * theta_k);
+      const bool cond2 = (fmaxf(theta_new, theta_k) < theta_min) && (slope < 0.f);
+      // jnp.maximum propagates NaN; fmaxf does not -> test explicitly
+      const bool cond2n = cond2 && !(theta_new != theta_new) && !(theta_k != theta_k);
+      const bool case2 = cond2n && (phi_new < phi_k + eta * alpha * slope);
+      const bool cond3 = !(cond1 || cond2n);
+      const bool case3 = cond3 && ((phi_new < phi_k - gamma_phi * phi_k) || (theta_new < (1.f - gamma_theta) * theta_k));
+      if (case1 || case2 || case3) best = i;  // descending loop keeps the smallest accepted index
+    }
+    s_idx = best;
+    s_alpha = exp2f(-float(best));
+    if (a.g_out) a.g_out[e] = phi_k;
+    if (a.alpha_index) a.alpha_index[e] = best;
+    if (a.iters) a.iters[e] = (a.first_iter ? 0 : a.iters[e]) + 1;
+    if (a.check_convergence && a.done) {
+      // mpc_wrapper.py:456-467: l2_cost = g*g at the NEW point; stop when last_cost - l2_cost < 1e-3 and sum c^2 < 1e-5
+      const float g_new = a.ls_phi[e * NALPHA + best];
+      const float c2_new = a.ls_theta[e * NALPHA + best];
+      const float l2 = g_new * g_new;
+      const float last = a.first_iter ? 1e10f : a.last_cost[e];
+      if ((last - l2 < 1e-3f) && (c2_new < 1e-5f)) a.done[e] = 1;
+      a.last_cost[e] = l2;
+    }
+  }
+  __syncthreads();
+  const float alpha = s_alpha;
+  const float* dX = a.dX + e * nx;
+  const float* dU = a.dU + e * nu;
+  const float* dV = a.dV + e * nx;
+  int bad = 0;
+  for (size_t i = tid; i < nx; i += blockDim.x) {
+    const float xv = fmaf(alpha, dX[i], Xi[i]);
+    const float vv = fmaf(alpha, dV[i], Vi[i]);
+    Xo[i] = xv;
+    Vo[i] = vv;
+    bad |= !(isfinite(xv) && isfinite(vv));
+  }
+  for (size_t i = tid; i < nu; i += blockDim.x) {
+    const float uv = fmaf(alpha, dU[i], Ui[i]);
+    Uo[i] = uv;
+    bad |= !isfinite(uv);
+  }
+  bad = __syncthreads_or(bad);
+  if (tid == 0 && a.status) a.status[e] = bad ? 1 : 0;
+}
+
+// update_and_extract_helper (mpc_wrapper.py:79-98 / 261-282) and the SRBD shift (mpc_wrapper_srbd.py:135-139)
+__global__ void shift_extract_kernel(int E, int N, int n, int m, int nj, int shift, int wb, const float* X,
+                                     const float* U, const float* V, const float* x0, const float* u_ref, float* X0,
+                                     float* U0, float* V0, float* tau, float* q, float* dq) {
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const size_t nx = size_t(N + 1) * n, nu = size_t(N) * m;
+  const float* Xe = X + e * nx;
+  const float* Ue = U + e * nu;
+  const float* Ve = V + e * nx;
+  float* X0e = X0 + e * nx;
+  float* U0e = U0 + e * nu;
+  float* V0e = V0 + e * nx;
+  const bool nan = wb && (Ue[0] != Ue[0]);  // jnp.isnan(U[0,0]); the SRBD wrapper has no guard
+  if (wb && tau) {
+    // safe: tau = U[0,:nj], q = X[0,7:7+nj], dq = X[1,13+nj:13+2nj]; unsafe: same rows of the PREVIOUS plan's row 1
+    for (int i = tid; i < nj; i += blockDim.x) {
+      tau[e * nj + i] = nan ? U0e[m + i] : Ue[i];
+      if (q) q[e * nj + i] = nan ? X0e[n + 7 + i] : Xe[7 + i];
+      if (dq) dq[e * nj + i] = nan ? X0e[n + 13 + nj + i] : Xe[n + 13 + nj + i];
+    }
+  }
+  __syncthreads();
+  if (nan) {
+    for (size_t i = tid; i < nx; i += blockDim.x) { X0e[i] = x0[size_t(e) * n + (i % n)]; V0e[i] = 0.f; }
+    for (size_t i = tid; i < nu; i += blockDim.x) U0e[i] = u_ref[i % m];
+    return;
+  }
+  for (size_t i = tid; i < nx; i += blockDim.x) {
+    const int t = int(i / n), j = int(i % n);
+    const int ts = min(t + shift, N);
+    X0e[i] = Xe[size_t(ts) * n + j];
+    V0e[i] = Ve[size_t(ts) * n + j];
+  }
+  for (size_t i = tid; i < nu; i += blockDim.x) {
+    const int t = int(i / m), j = int(i % m);
+    const int ts = min(t + shift, N - 1);
+    U0e[i] = Ue[size_t(ts) * m + j];
+  }
+}
+
+}  // namespace mpxb

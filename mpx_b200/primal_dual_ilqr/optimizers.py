@@ -1,0 +1,226 @@
+"""``optimizers.mpc`` -- the reference's solver entry point, served by libmpxb.so.
+
+Reference: mpx/primal_dual_ilqr/primal_dual_ilqr/optimizers.py:603-683.  The positional signature is kept::
+
+    work = partial(optimizers.mpc, cost, dynamics, hessian_approx, limited_memory)
+    X, U, V = work(reference, parameter, W, x0, X_in, U_in, V_in)
+
+``cost`` / ``dynamics`` / ``hessian_approx`` are the descriptor partials the wrappers build exactly like the
+reference builds its function partials (mpc_wrapper.py:66-74, mpc_wrapper_srbd.py:60-68); their bound arguments
+carry the dimensions and model tables from which the CUDA model handle is created (once, cached).
+Inputs are torch CUDA float32 tensors, either per-environment ([N+1, n] ...) or batched with a leading env
+axis ([E, N+1, n] ...) -- the batch axis replaces the reference's ``jax.vmap(work)`` (mpc_wrapper_srbd.py:77,
+examples/multi_env.py:46-49).  There is no CPU path: non-CUDA tensors raise.
+"""
+import ctypes as C
+from functools import partial
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils.models import DynamicsKind
+from ..utils.objectives import ObjectiveKind
+
+
+class _Cfg:
+    """Minimal config namespace rebuilt from descriptor partials."""
+
+
+def _unwrap(p):
+    args = ()
+    while isinstance(p, partial):
+        args = p.args + args
+        p = p.func
+    return p, args
+
+
+class MpcSolver:
+    """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
+
+    def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_env = int(n_env)
+        self.lq_mode = _lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN
+        self.max_iter = int(max_iter)
+        self.desc = _lib.make_desc(config, robot_model)
+        self.N, self.n, self.m = self.desc.N, self.desc.n, self.desc.m
+        self.nref, self.npar, self.nw = self.desc.nref, self.desc.npar, self.desc.nw
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mpxb_model_create(C.byref(self.desc), C.byref(handle)), "mpxb_model_create")
+        self.handle = handle
+        self.ws_bytes = self.lib.mpxb_workspace_bytes(self.handle, self.n_env, self.lq_mode)
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        E = self.n_env
+        self.alpha_index = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.iters = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(E, dtype=torch.int32, device=self.device)
+        self.launches_per_call = 4 * self.max_iter
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mpxb_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _chk(self, t, shape, name):
+        if not (torch.is_tensor(t) and t.is_cuda):
+            raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} != {tuple(shape)}")
+        return t
+
+    def solve(self, reference, parameter, W, x0, X_in, U_in, V_in, out=None):
+        """Batched call: every argument carries the leading env axis except W ([nw,nw] shared or [E,nw,nw])."""
+        E, N, n, m = self.n_env, self.N, self.n, self.m
+        reference = self._chk(reference, (E, N + 1, self.nref), "reference")
+        parameter = self._chk(parameter, (E, N + 1, self.npar), "parameter")
+        if W.dim() == 2:
+            W = self._chk(W, (self.nw, self.nw), "W")
+            wstride = 0
+        else:
+            W = self._chk(W, (E, self.nw, self.nw), "W")
+            wstride = self.nw * self.nw
+        x0 = self._chk(x0, (E, n), "x0")
+        X_in = self._chk(X_in, (E, N + 1, n), "X_in")
+        U_in = self._chk(U_in, (E, N, m), "U_in")
+        V_in = self._chk(V_in, (E, N + 1, n), "V_in")
+        if out is None:
+            X = torch.empty_like(X_in)
+            U = torch.empty_like(U_in)
+            V = torch.empty_like(V_in)
+        else:
+            X, U, V = out
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpxb_mpc_step(
+            self.handle, stream, E, self.lq_mode, self.max_iter,
+            reference.data_ptr(), parameter.data_ptr(), W.data_ptr(), wstride,
+            x0.data_ptr(), X_in.data_ptr(), U_in.data_ptr(), V_in.data_ptr(),
+            X.data_ptr(), U.data_ptr(), V.data_ptr(),
+            self.alpha_index.data_ptr(), self.iters.data_ptr(), self.status.data_ptr(),
+            self.workspace.data_ptr(), self.ws_bytes)
+        _lib.check(rc, "mpxb_mpc_step")
+        return X, U, V
+
+    def view(self, name):
+        """Intermediate of the last call (A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, ls_theta, ls_phi, g, cost, slope)."""
+        cnt = C.c_size_t()
+        ptr = self.lib.mpxb_workspace_view(self.handle, self.n_env, self.lq_mode, self.workspace.data_ptr(),
+                                           name.encode(), C.byref(cnt))
+        if not ptr:
+            raise KeyError(name)
+        off = ptr - self.workspace.data_ptr()
+        flat = self.workspace[off:off + 4 * cnt.value].view(torch.float32)
+        E, N, n, m = self.n_env, self.N, self.n, self.m
+        shapes = {"A": (E, N, n, n), "B": (E, N, n, m), "Q": (E, N + 1, n, n), "R": (E, N, m, m), "M": (E, N, n, m),
+                  "q": (E, N + 1, n), "r": (E, N, m), "c": (E, N + 1, n), "K": (E, N, m, n), "k": (E, N, m),
+                  "P": (E, N + 1, n, n), "p": (E, N + 1, n), "dX": (E, N + 1, n), "dU": (E, N, m),
+                  "dV": (E, N + 1, n), "ls_theta": (E, 11), "ls_phi": (E, 11), "g": (E,), "cost": (E, N + 1),
+                  "slope": (E,)}
+        return flat.view(shapes[name])
+
+    def shift_extract(self, X, U, V, x0, u_ref, X0, U0, V0, shift, want_cmd=True):
+        """update_and_extract_helper (mpc_wrapper.py:79-98): in-place update of the warm start (X0,U0,V0)."""
+        E, nj = self.n_env, self.desc.n_joints
+        wb = self.desc.kind != _lib.KIND_SRBD
+        tau = q = dq = None
+        if wb and want_cmd:
+            tau = torch.empty(E, nj, dtype=torch.float32, device=self.device)
+            q = torch.empty_like(tau)
+            dq = torch.empty_like(tau)
+        p = lambda t: t.data_ptr() if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpxb_shift_extract(self.handle, stream, E, int(shift), p(X), p(U), p(V), p(x0), p(u_ref),
+                                         p(X0), p(U0), p(V0), p(tau), p(q), p(dq))
+        _lib.check(rc, "mpxb_shift_extract")
+        return tau, q, dq
+
+
+_SOLVERS = {}
+
+
+def _config_from_partials(cost, dynamics, hessian_approx):
+    """Rebuild the numeric config from the bound arguments of the descriptor partials."""
+    dyn, dargs = _unwrap(dynamics)
+    obj, cargs = _unwrap(cost)
+    if not isinstance(dyn, DynamicsKind) or not isinstance(obj, ObjectiveKind):
+        raise TypeError("mpc() expects the descriptor partials built by the mpx_b200 wrappers "
+                        "(arbitrary Python cost/dynamics callables cannot run on the CUDA path)")
+    cfg = _Cfg()
+    cfg.dynamics, cfg.cost, cfg.hessian_approx = dyn, obj, hessian_approx
+    if dyn.kind == _lib.KIND_SRBD:
+        # partial(quadruped_srbd_dynamics, mass, inertia, inertia_inv, dt); partial(srbd_obj, n_contact, N)
+        cfg.mass, cfg.inertia, _, cfg.dt = dargs[:4]
+        cfg.n_contact, cfg.N = cargs[-2:]
+        cfg.n_joints = 3 * cfg.n_contact
+        cfg.n, cfg.m = 13, 3 * cfg.n_contact
+        cfg.W = np.zeros((12 + 3 * cfg.n_contact,) * 2)
+        robot_model = None
+    else:
+        # partial(dynamics, model, mjx_model, contact_id, body_id, n_joints, dt); partial(cost, [flag], nj, nc, N)
+        robot_model, _, contact_names, body_names, cfg.n_joints, cfg.dt = dargs[:6]
+        cfg.n_joints, cfg.n_contact, cfg.N = cargs[-3:]
+        cfg.contact_frame, cfg.body_name = contact_names, body_names
+        if len(cargs) > 3:
+            cfg.cost = partial(obj, *cargs[:-3])
+        nj, nc = cfg.n_joints, cfg.n_contact
+        grf_in_u = dyn.kind == _lib.KIND_TALOS_WB
+        cfg.n = 13 + 2 * nj + (3 * nc if grf_in_u else 6 * nc)
+        cfg.m = nj + (3 * nc if grf_in_u else 0)
+        cfg.W = np.zeros((12 + 3 * nj + 6 * nc,) * 2)
+    return cfg, robot_model
+
+
+def mpc(cost, dynamics, hessian_approx, limited_mempory, reference, parameter, W, x0, X_in, U_in, V_in):
+    """Drop-in for reference optimizers.mpc (optimizers.py:603-683); see the module docstring."""
+    batched = reference.dim() == 3
+    if not batched:
+        reference, parameter, x0, X_in, U_in, V_in = (t.unsqueeze(0) for t in (reference, parameter, x0, X_in, U_in, V_in))
+    E = reference.shape[0]
+    key = (id(_unwrap(cost)[0]), _unwrap(cost)[1][-3:], id(_unwrap(dynamics)[0]), id(_unwrap(dynamics)[1][0]),
+           bool(limited_mempory), E, reference.device.index)
+    solver = _SOLVERS.get(key)
+    if solver is None:
+        cfg, rm = _config_from_partials(cost, dynamics, hessian_approx)
+        solver = MpcSolver(cfg, E, bool(limited_mempory), device=reference.device, robot_model=rm)
+        _SOLVERS[key] = solver
+    X, U, V = solver.solve(reference, parameter, W, x0, X_in, U_in, V_in)
+    if not batched:
+        X, U, V = X[0], U[0], V[0]
+    return X, U, V
+
+
+def tvlqr_solve(Q, q, R, r, M, A, B, c, limited_memory=True):
+    """Batched LQ sub-problem on the GPU: tvlqr+rollout+dual_lqr (limited_memory=True) or the scan forms.
+
+    Reference: compute_search_direction's LQ half (optimizers.py:175-182).  All inputs [E, ...] CUDA float32;
+    ``c`` is [E, N+1, n] (c[:,0] = rollout start, c[:,1:] = offsets).  Returns K, k, P, p, dX, dU, dV, slope.
+    """
+    lib = _lib.lib()
+    for t in (Q, q, R, r, M, A, B, c):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("tvlqr_solve expects contiguous float32 CUDA tensors")
+    E, N, n, m = B.shape
+    dev = Q.device
+    mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    K, k, P, p = mk(E, N, m, n), mk(E, N, m), mk(E, N + 1, n, n), mk(E, N + 1, n)
+    dX, dU, dV, slope = mk(E, N + 1, n), mk(E, N, m), mk(E, N + 1, n), mk(E)
+    mode = _lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN
+    scan = None
+    if not limited_memory:
+        scan = torch.empty(max(lib.mpxb_tvlqr_scan_bytes(E, N, n, m), 4), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.mpxb_tvlqr(stream, E, N, n, m, mode, Q.data_ptr(), q.data_ptr(), R.data_ptr(), r.data_ptr(),
+                        M.data_ptr(), A.data_ptr(), B.data_ptr(), c.data_ptr(), K.data_ptr(), k.data_ptr(),
+                        P.data_ptr(), p.data_ptr(), dX.data_ptr(), dU.data_ptr(), dV.data_ptr(), slope.data_ptr(),
+                        scan.data_ptr() if scan is not None else None)
+    _lib.check(rc, "mpxb_tvlqr")
+    return K, k, P, p, dX, dU, dV, slope

@@ -1,0 +1,95 @@
+"""SRBD batched MPC wrapper -- same class/constructor/``run``/``reset`` as reference
+``mpx/utils/mpc_wrapper_srbd.py:19-175`` with the jitted JAX solve replaced by libmpxb.so.
+
+State lives in torch CUDA tensors; ``run`` enqueues the gait timer, the reference generator, the solve and the
+warm-start shift on the current CUDA stream and never synchronises.
+"""
+from functools import partial
+
+import numpy as np
+import torch
+
+import mpx_b200.utils.mpc_utils as mpc_utils
+import mpx_b200.utils.models as mpc_dyn_model
+import mpx_b200.utils.objectives as mpc_objectives
+import mpx_b200.primal_dual_ilqr.optimizers as optimizers
+
+
+class BatchedMPCControllerWrapper:
+    def __init__(self, config, n_env, device=None):
+        """reference mpc_wrapper_srbd.py:20-96."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("mpx_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=self.device)
+        self._T = T
+        self.n_env = n_env
+        self.config = config
+        self.mpc_frequency = config.mpc_frequency
+        self.shift = int(1 / (config.dt * config.mpc_frequency))
+        self.foot0 = np.array(config.p_legs0, dtype=np.float64)
+        self.q0 = np.array(config.q0, dtype=np.float64)
+        self.initial_state = T(np.concatenate([config.p0, config.quat0, np.zeros(6)]))
+
+        # cost / hessian / dynamics partials, bound exactly like the reference (mpc_wrapper_srbd.py:60-68)
+        cost = partial(mpc_objectives.quadruped_srbd_obj, config.n_contact, config.N)
+        hessian_approx = partial(mpc_objectives.quadruped_srbd_hessian_gn, config.n_contact)
+        inertia = np.asarray(config.inertia, dtype=np.float64)
+        dynamics = partial(mpc_dyn_model.quadruped_srbd_dynamics, config.mass, inertia, np.linalg.inv(inertia), config.dt)
+        self.work = partial(optimizers.mpc, cost, dynamics, hessian_approx, False)
+        # the batch axis of the CUDA solver replaces jax.jit(jax.vmap(work)) (mpc_wrapper_srbd.py:77)
+        self._solver = optimizers.MpcSolver(config, n_env, limited_memory=False, device=self.device)
+        self._solve = self._solver.solve
+        self._ref_gen = partial(mpc_utils.reference_generator_srbd, config.use_terrain_estimator, config.N, config.dt,
+                                config.n_contact, mass=config.mass, clearence_speed=config.clearence_speed,
+                                duty_factor=config.duty_factor, step_freq=config.step_freq,
+                                step_height=config.step_height, foot0=config.p_legs0)
+        self._timer_run = mpc_utils.timer_run
+        self.W = T(config.W)
+        self.u_ref = T(config.u_ref)
+        self.reset(verbose=False)
+        self.foot_ref = torch.zeros(n_env, 3 * config.n_contact, device=self.device)
+        self.foot_ref_dot = torch.zeros(n_env, 3 * config.n_contact, device=self.device)
+        self.grf = torch.zeros(n_env, 3 * config.n_contact, device=self.device)
+
+    def run(self, x0, input, foot_op, contact):
+        """One MPC update (mpc_wrapper_srbd.py:91-141). All arguments [n_env, ...] CUDA tensors."""
+        x0, input, foot_op, contact = (self._as(t) for t in (x0, input, foot_op, contact))
+        self.contact, self.contact_time = self._timer_run(self.config.duty_factor, self.config.step_freq,
+                                                          self.contact_time, 1 / self.mpc_frequency)
+        reference, parameter, self.liftoff, foot_ref_dot = self._ref_gen(
+            t_timer=self.contact_time.clone(), x=x0, foot=foot_op, input=input, contact=contact, liftoff=self.liftoff)
+        self.foot_ref = parameter[:, 0, 4:]
+        self.foot_ref_dot = foot_ref_dot[:, 0, :]
+        X, U, V = self._solve(reference, parameter, self.W, x0, self.batch_X0, self.batch_U0, self.batch_V0)
+        # warm start for the next call (mpc_wrapper_srbd.py:135-137), fused shift kernel
+        self._solver.shift_extract(X, U, V, x0, self.u_ref, self.batch_X0, self.batch_U0, self.batch_V0, self.shift)
+        self.grf = U[:, 0, :]
+        self.X, self.U, self.V = X, U, V
+        return 0
+
+    def _as(self, t):
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t), dtype=torch.float32)
+        return t.to(device=self.device, dtype=torch.float32, non_blocking=True)
+
+    def torch_run(self, x0_torch, input_torch, foot_op_torch, contact_torch=None):
+        """mpc_wrapper_srbd.py:143-151 (the reference passes 3 arguments to a 4-argument run; contact defaults to 1)."""
+        if contact_torch is None:
+            contact_torch = torch.ones(self.n_env, self.config.n_contact, device=self.device)
+        return self.run(x0_torch, input_torch, foot_op_torch, contact_torch)
+
+    def whole_body_run(self, qpos, qvel):
+        raise NotImplementedError("whole_body_interface (mpc_utils.py:275-313) is outside the solve path (SURVEY.md 8f-3)")
+
+    def reset(self, verbose=True):
+        """mpc_wrapper_srbd.py:162-174."""
+        cfg, E = self.config, self.n_env
+        self.contact_time = self._T(cfg.timer_t).repeat(E, 1)
+        self.liftoff = torch.zeros(E, 3 * cfg.n_contact, device=self.device)
+        self.batch_U0 = self.u_ref.repeat(E, cfg.N, 1).contiguous()
+        self.batch_X0 = self.initial_state.repeat(E, cfg.N + 1, 1).contiguous()
+        self.batch_V0 = torch.zeros(E, cfg.N + 1, cfg.n, device=self.device)
+        if verbose:
+            print("MPC Controller Reset")
+        return

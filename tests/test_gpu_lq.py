@@ -1,0 +1,66 @@
+"""GPU parity of the LQ kernels (mpxb_tvlqr through the C ABI) against the float64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import primal_dual_ilqr as pdi
+from lq_problems import simple_lqr_problem, random_lq
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_gpu(prob, E):
+    Q, q, R, r, M, A, B, c, x0 = prob
+    cc = torch.cat([x0[None], c], 0)
+    f = lambda t: t.to(torch.float32).unsqueeze(0).repeat(E, *([1] * t.dim())).contiguous().cuda()
+    return tuple(f(t) for t in (Q, q, R, r, M, A, B, cc))
+
+
+def _oracle(prob, scan):
+    Q, q, R, r, M, A, B, c, x0 = prob
+    if scan:
+        K, k, P, p = pdi.tvlqr_gpu(Q, q, R, r, M, A, B, c)
+        dX, dU = pdi.rollout_gpu(K, k, x0, A, B, c)
+    else:
+        K, k, P, p = pdi.tvlqr(Q, q, R, r, M, A, B, c)
+        dX, dU = pdi.rollout(K, k, x0, A, B, c)
+    dV = pdi.dual_lqr(dX, P, p)
+    slope = torch.sum(q * dX) + torch.sum(r * dU)
+    return K, k, P, p, dX, dU, dV, slope
+
+
+def _check(got, want, tol):
+    names = ["K", "k", "P", "p", "dX", "dU", "dV", "slope"]
+    for nm, g, w in zip(names, got, want):
+        g = g[0].double().cpu()
+        scale = max(1.0, float(w.abs().max()))
+        err = float((g - w).abs().max()) / scale
+        assert err < tol, f"{nm}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("limited_memory", [True, False])
+def test_reference_simple_lqr_problem(limited_memory):
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    prob = simple_lqr_problem()
+    got = tvlqr_solve(*_to_gpu(prob, 3), limited_memory=limited_memory)
+    _check(got, _oracle(prob, not limited_memory), 2e-5)
+
+
+@pytest.mark.parametrize("n,m,T", [(4, 1, 50), (8, 2, 30), (13, 12, 25), (61, 12, 25), (75, 19, 25), (81, 46, 25), (81, 46, 60)])
+@pytest.mark.parametrize("limited_memory", [True, False])
+def test_random_lq(n, m, T, limited_memory):
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    prob = random_lq(n, m, T, seed=n + T)
+    got = tvlqr_solve(*_to_gpu(prob, 2), limited_memory=limited_memory)
+    # FP32 budget: the float32 oracle's own error against float64 is ~1e-5 on these problems
+    _check(got, _oracle(prob, not limited_memory), 2e-4)
+    # batch entries are independent and identical
+    for g in got:
+        assert torch.equal(g[0], g[1])
+
+
+def test_unsupported_dims_rejected():
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    prob = random_lq(5, 3, 4, seed=1)
+    with pytest.raises(RuntimeError, match="UNSUPPORTED"):
+        tvlqr_solve(*_to_gpu(prob, 1), limited_memory=True)
