@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- batched MPC solves/sec of the B200-native primal-dual iLQR path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # native arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (restated reference on host cores)
+
+A "step" is one pass of the hot path over one batch of synthetic robot states: one `optimizers.mpc` call
+(evaluate + linearise/quadratise + LQ solve + 11-alpha filter line search) for every environment, followed by
+the warm-start shift, in closed loop on the model (x0 <- X[shift]).  Workload at N=1: Go2 whole-body MPC,
+1024 environments per GPU (BASELINE.json configs[2]); with N>1 every rank owns its own 1024-environment slice
+(weak scaling, no collective on the solve path, one final gather of the controls).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched MPC solves/sec"
+UNIT = "solves/s"
+WORKLOADS = {
+    "go2_wb": ("go2", "Go2 whole-body batched MPC (examples/multi_env.py with config_go2), sequential LQ (limited_memory=True)"),
+    "aliengo_wb": ("aliengo", "Aliengo whole-body MPC (examples/mjx_quad.py)"),
+    "h1_wb": ("h1", "H1 whole-body batched MPC"),
+    "talos_wb": ("talos", "Talos whole-body MPC (examples/mjx_talos.py)"),
+    "srbd": ("srbd", "Aliengo SRBD MPC (examples/srbd_quad.py)"),
+}
+
+
+def f_lqr(n, m, N):
+    """Algorithmic FLOPs of one LQ solve: sequential Riccati + rollout + dual, FMA = 2."""
+    return (N * (4 * n ** 3 + 6 * m * n ** 2 + 2 * m ** 2 * n + m ** 3 / 3 + 2 * m ** 2 * (n + 1) + 4 * n ** 2 + 6 * m * n)
+            + N * (2 * n ** 2 + 4 * m * n) + (N + 1) * 2 * n ** 2)
+
+
+def lq_bytes(n, m, N):
+    """Algorithmic HBM bytes of the LQ kernel per solve: read A,B,Q,R,M,q,r,c once, write K,k,P,p,dX,dU,dV once."""
+    rd = N * (n * n + n * m + m * m + n * m + m) + (N + 1) * (n * n + 2 * n)
+    wr = N * (m * n + m + m) + (N + 1) * (n * n + 3 * n)
+    return 4 * (rd + wr)
+
+
+def synthetic_states(cfg, E, seed):
+    """SURVEY.md 8(d) synthetic robot states + commands (numpy float32)."""
+    rng = np.random.default_rng(seed)
+    nj = cfg.n_joints
+    dz = rng.uniform(-0.02, 0.02, E)
+    rpy = rng.uniform(-0.1, 0.1, (E, 3))
+    cr, sr = np.cos(rpy[:, 0] / 2), np.sin(rpy[:, 0] / 2)
+    cp, sp = np.cos(rpy[:, 1] / 2), np.sin(rpy[:, 1] / 2)
+    cy, sy = np.cos(rpy[:, 2] / 2), np.sin(rpy[:, 2] / 2)
+    quat = np.stack([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                     cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy], 1)
+    p = np.tile(np.asarray(cfg.p0, dtype=np.float64), (E, 1))
+    p[:, 2] += dz
+    q = np.asarray(cfg.q0, dtype=np.float64)[None] + rng.uniform(-0.05, 0.05, (E, nj))
+    v = rng.uniform(-0.2, 0.2, (E, 3))
+    w = rng.uniform(-0.2, 0.2, (E, 3))
+    dq = rng.uniform(-0.5, 0.5, (E, nj))
+    cmd = np.stack([rng.uniform(-0.2, 0.5, E), rng.uniform(-0.1, 0.1, E), np.zeros(E), np.zeros(E), np.zeros(E),
+                    rng.uniform(-0.3, 0.3, E), np.full(E, cfg.robot_height)], 1)
+    phase = rng.uniform(0, 1, (E, 1))
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(qpos=f32(np.concatenate([p, quat, q], 1)), qvel=f32(np.concatenate([v, w, dq], 1)), cmd=f32(cmd),
+                timer=f32(np.mod(np.asarray(cfg.timer_t)[None] + phase, 1.0)), yaw=rpy[:, 2])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if "Active" in val and "Not" not in val:
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def _cpu_solve_worker(args):
+    """One restated-reference `optimizers.mpc` call (float32 torch oracle) for one environment."""
+    robot, seed = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle.problems import Problem, synthetic_inputs
+    cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
+    key = ("pr", robot)
+    if key not in _cpu_solve_worker.__dict__:
+        _cpu_solve_worker.__dict__[key] = Problem(cfg, dtype=torch.float32)
+    pr = _cpu_solve_worker.__dict__[key]
+    inp = synthetic_inputs(pr, 1, seed=seed)
+    t0 = time.perf_counter()
+    pr.mpc(True, inp["reference"][0], inp["parameter"][0], inp["x0"][0], inp["X0"][0], inp["U0"][0], inp["V0"][0])
+    return time.perf_counter() - t0
+
+
+def cpu_arm(robot, steps, warmup, cores):
+    """Times the oracle port on the host cores: each step = `cores` independent solves, one per process."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        seed = 1000
+        for _ in range(warmup):
+            pool.map(_cpu_solve_worker, [(robot, seed + i) for i in range(cores)])
+            seed += cores
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_solve_worker, [(robot, seed + i) for i in range(cores)])
+            seed += cores
+        dt = time.perf_counter() - t0
+    return cores * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    robot, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    # bounded sample: the pure-Python/torch restatement needs ~10-20 s per whole-body solve per core, so the
+    # number of timed steps is capped to keep the run within minutes (stated in `sample`)
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    warmup = min(args.warmup, 1)
+    value, ms = cpu_arm(robot, steps, warmup, cores)
+    sample = (f"{cores} independent solves per step (one per process), {steps} timed steps after {warmup} warm-up; "
+              f"float32 torch restatement of the reference (JAX/MJX not installable here)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "robot": robot, "envs_per_step": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from mpx_b200 import _lib
+    from mpx_b200.utils.mpc_wrapper import BatchedMPCControllerWrapper
+    from mpx_b200.utils.mpc_wrapper_srbd import BatchedMPCControllerWrapper as SrbdWrapper
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py native arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    robot, desc = WORKLOADS[args.workload]
+    cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
+    E, K, Wm = args.envs, args.steps, args.warmup
+    srbd = robot == "srbd"
+    lib = _lib.lib()
+    st = synthetic_states(cfg, E, seed=rank)
+    T = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
+    N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
+    lm = not args.scan
+
+    if srbd:
+        wrap = SrbdWrapper(cfg, E, device=dev)
+        solver = wrap._solver if not lm else __import__("mpx_b200.primal_dual_ilqr.optimizers", fromlist=["MpcSolver"]).MpcSolver(cfg, E, True, device=dev)
+        yaw = st["yaw"]
+        Ry = np.stack([np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw], 1), np.stack([np.sin(yaw), np.cos(yaw), 0 * yaw], 1),
+                       np.stack([0 * yaw, 0 * yaw, 1 + 0 * yaw], 1)], 1)
+        base = np.concatenate([st["qpos"][:, :2], np.zeros((E, 1))], 1)
+        feet = T((base[:, None, :] + np.einsum("eij,fj->efi", Ry, np.asarray(cfg.p_legs0).reshape(nc, 3))).reshape(E, -1))
+        x0 = T(np.concatenate([st["qpos"][:, :7], st["qvel"][:, :6]], 1))
+        wrap.contact_time = T(st["timer"])
+        wrap.liftoff = feet.clone()
+    else:
+        wrap = BatchedMPCControllerWrapper(cfg, E, limited_memory=lm, device=dev)
+        solver = wrap._solver
+        qpos, qvel = T(st["qpos"]), T(st["qvel"])
+        feet = wrap.foot_positions(qpos)
+        data = wrap.reset(wrap.make_data(), qpos, qvel, feet)
+        data = data.replace(contact_time=T(st["timer"]))
+        x0 = data.X0[:, 0, :].clone()
+    Wt = T(cfg.W)
+    u_ref = T(cfg.u_ref)
+    shift = int(1 / (cfg.dt * cfg.mpc_frequency))
+    n_warm = max(Wm, 3)
+    # ---- input tape: the real closed loop (gait timer + reference generator + solve + shift, x0 <- X[shift]) is run
+    # once, untimed, for n_warm + K ticks and its per-tick solve inputs (reference, parameter, x0) are kept in HBM.
+    # The timed loop replays the tape through the solve + shift kernels only; every kernel is deterministic, so the
+    # replay reproduces the closed-loop iterates exactly.
+    tape = []
+    if srbd:
+        for _ in range(n_warm + K):
+            wrap.run(x0, T(st["cmd"]), feet, torch.ones(E, nc, device=dev))
+            tape.append((wrap.reference, wrap.parameter, x0))
+            x0 = wrap.X[:, shift, :].clone()
+            feet = wrap.parameter[:, 0, 4:].clone()
+        x_init = tape[0][2]
+        X0 = wrap.initial_state.repeat(E, N + 1, 1).contiguous()
+    else:
+        cmd = T(st["cmd"])
+        d = data
+        for _ in range(n_warm + K):
+            d, _ = wrap.run(d, x0, cmd)
+            tape.append((wrap.reference, wrap.parameter, x0))
+            x0 = wrap.X[:, shift, :].clone()
+        x_init = tape[0][2]
+        X0 = x_init[:, None, :].repeat(1, N + 1, 1).contiguous()
+    U0 = u_ref.repeat(E, N, 1).contiguous()
+    V0 = torch.zeros(E, N + 1, n, device=dev)
+    X, U, V = torch.empty_like(X0), torch.empty_like(U0), torch.empty_like(V0)
+    tape_pos = [0]
+
+    def step():
+        reference, parameter, x0c = tape[tape_pos[0]]
+        tape_pos[0] += 1
+        solver.solve(reference, parameter, Wt, x0c, X0, U0, V0, out=(X, U, V))
+        solver.shift_extract(X, U, V, x0c, u_ref, X0, U0, V0, shift, want_cmd=False)
+    launches_per_step = 4 * solver.max_iter + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(n_warm):
+        step()
+    prof = C.c_void_p()
+    _lib.check(lib.mpxb_profile_create(K, C.byref(prof)), "mpxb_profile_create")
+    _lib.check(lib.mpxb_profile_attach(solver.handle, prof), "mpxb_profile_attach")
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    kms = (C.c_double * 4)()
+    ncalls = C.c_int()
+    _lib.check(lib.mpxb_profile_read(prof, C.byref(kms), C.byref(ncalls)), "mpxb_profile_read")
+    lib.mpxb_profile_attach(solver.handle, None)
+    lib.mpxb_profile_destroy(prof)
+    nonfinite_envs = int((~torch.isfinite(X).flatten(1).all(1)).sum().item())
+    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total = float(tms.item())
+
+    # ---- end to end through the wrapper API with HOST buffers (H2D of x0 / command, D2H of the torques every step)
+    e2e = None
+    if not srbd:
+        x0_h = torch.empty(E, n, dtype=torch.float32).pin_memory()
+        cmd_h = torch.as_tensor(st["cmd"]).pin_memory()
+        tau_h = torch.empty(E, nj, dtype=torch.float32).pin_memory()
+        x0_h.copy_(x_init.cpu())
+        d2 = wrap.reset(wrap.make_data(), qpos, qvel, feet).replace(contact_time=T(st["timer"]))
+
+        def tick(d):
+            xd = x0_h.to(dev, non_blocking=True)
+            cd = cmd_h.to(dev, non_blocking=True)
+            d, tau = wrap.run(d, xd, cd)
+            tau_h.copy_(tau, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()     # the caller reads tau
+            x0_h.copy_(wrap.X[:, shift, :], non_blocking=True)   # simulator stand-in: next measured state (not counted)
+            return d
+        for _ in range(max(Wm, 3)):
+            d2 = tick(d2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            d2 = tick(d2)
+        e1.record()
+        barrier()
+        t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": E * world * K / (float(t_e2e.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(E * (n + 7) * 4), "d2h_bytes_per_step": int(E * nj * 4),
+               "ms_per_step": float(t_e2e.item()) / K,
+               "api": "BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
+
+    # final gather of the controls (the only collective; north_star), outside the timed solve path
+    if world > 1:
+        tau = U[:, 0, :nj].contiguous()
+        out = [torch.empty_like(tau) for _ in range(world)] if rank == 0 else None
+        dist.gather(tau, out, dst=0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp32_peak = float(lib.mpxb_fp32_peak_tflops(None, 2048))
+        names = ["linearize", "lq_solve", "trial", "select"]
+        kernel_ms = {nm: float(kms[i]) for i, nm in enumerate(names)}
+        dom = max(kernel_ms, key=kernel_ms.get)
+        flq = f_lqr(n, m, N) * E
+        blq = lq_bytes(n, m, N) * E
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(args.workload, {}).get("lq_solve_dram_bytes_per_launch")
+        except Exception:
+            pass
+        lq_s = kernel_ms["lq_solve"] * 1e-3
+        roofline = {"kernel": "lq_seq_kernel" if lm else "lq_scan", "bound": "fp32",
+                    "achieved": flq / lq_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": flq / lq_s / 1e12 / fp32_peak, "traffic": traffic,
+                    "peak_source": "FP32 FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                    "algorithmic": f"F_lqr(n={n},m={m},N={N}) = {f_lqr(n, m, N) / 1e6:.2f} MFLOP per solve x {E} solves per launch",
+                    "hbm": {"achieved": blq / lq_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                            "frac": (blq / lq_s / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                            "algorithmic": f"{lq_bytes(n, m, N) / 1e6:.3f} MB per solve (LQ data read once + outputs written once)"},
+                    "kernel_ms": kernel_ms, "dominant_kernel": dom,
+                    "share_of_step": {k: v / (ms_total / K) for k, v in kernel_ms.items()}}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, ms = cpu_arm(robot, 1, 0, cores)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{cores} solves of the same workload, one per process (float32 torch restatement of the reference)"}
+        line = {"metric": METRIC, "value": E * world * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": max(Wm, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "robot": robot, "envs_per_gpu": E, "n": n, "m": m, "horizon": N,
+                           "lq": "sequential" if lm else "scan", "sqp_iterations_per_step": 1,
+                           "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
+                           "parallelism": f"env-sharded x{world}, no collective on the solve path"},
+                "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "clocks": clocks, "nonfinite_envs": nonfinite_envs}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="go2_wb", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
+    ap.add_argument("--scan", action="store_true", help="associative-scan LQ (limited_memory=False)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-max-steps", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,22 @@ int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const floa
                float* K, float* k, float* P, float* p, float* dX, float* dU, float* dV, float* slope, void* scan_ws);
 size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m);
 
+/* Foot (contact sphere) positions by forward kinematics, batched: qpos [E, 7 + n_joints] -> feet [E, 3 * n_contact].
+ * Replaces the host-side MuJoCo mj_kinematics + geom_xpos read of mpc_wrapper.py:313-318 / 373-376 (whole-body kinds). */
+int mpxb_wb_foot_positions(const mpxb_model* model, void* stream, int E, const float* qpos, float* feet);
+
+/* Per-kernel timing for benchmarks (bench.py roofline): once attached, every mpxb_mpc_step on `model` records CUDA
+ * events on its stream at the boundaries of the four kernels of the LAST SQP iteration of the call
+ * (linearise | LQ solve | line-search trials | select/update).  Up to `max_calls` calls are kept (later calls are
+ * not recorded).  mpxb_profile_read synchronises on the recorded events and returns the MEAN duration in
+ * milliseconds of each of the four kernels over the recorded calls.  Attaching mutates the handle: benchmarking
+ * only, not thread-safe.  Pass profile = NULL to detach. */
+typedef struct mpxb_profile mpxb_profile;
+int mpxb_profile_create(int max_calls, mpxb_profile** out);
+void mpxb_profile_destroy(mpxb_profile* profile);
+int mpxb_profile_attach(mpxb_model* model, mpxb_profile* profile);
+int mpxb_profile_read(mpxb_profile* profile, double mean_ms[4], int* calls);
+
 /* FP32 FFMA throughput micro-benchmark (roofline denominator).  Returns TFLOP/s measured with
  * CUDA events on `stream`, or a negative MPXB_E*. */
 double mpxb_fp32_peak_tflops(void* stream, int iters);

@@ -65,6 +65,16 @@ def lib():
     L.mpxb_tvlqr.restype = i32
     L.mpxb_tvlqr_scan_bytes.argtypes = [i32, i32, i32, i32]
     L.mpxb_tvlqr_scan_bytes.restype = sz
+    L.mpxb_wb_foot_positions.argtypes = [vp, vp, i32, f32p, f32p]
+    L.mpxb_wb_foot_positions.restype = i32
+    L.mpxb_profile_create.argtypes = [i32, C.POINTER(vp)]
+    L.mpxb_profile_create.restype = i32
+    L.mpxb_profile_destroy.argtypes = [vp]
+    L.mpxb_profile_destroy.restype = None
+    L.mpxb_profile_attach.argtypes = [vp, vp]
+    L.mpxb_profile_attach.restype = i32
+    L.mpxb_profile_read.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(i32)]
+    L.mpxb_profile_read.restype = i32
     L.mpxb_fp32_peak_tflops.argtypes = [vp, i32]
     L.mpxb_fp32_peak_tflops.restype = C.c_double
     _lib = L

@@ -20,8 +20,14 @@
 
 using namespace mpxb;
 
+struct mpxb_profile {
+  int max_calls, calls;
+  cudaEvent_t* ev;  // 5 per call
+};
+
 struct mpxb_model {
   mpxb_model_desc desc;
+  mpxb_profile* prof;
   SrbdParams srbd;
   WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
   WbModel wb_host;
@@ -65,6 +71,16 @@ bool lq_supported(int n, int m) {
   return false;
 }
 
+template <int NB, int NV, int NC>
+__global__ void wb_feet_kernel(const WbModel* __restrict__ mdp, int E, const float* __restrict__ qpos, float* __restrict__ feet) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const WbModel& md = *mdp;
+  float xpos[NB][3], xquat[NB][4], cinert[NB][10], cdof[NV][6], com[3], f[3 * NC];
+  wb_geometry<float, NB, NV, NC>(md, qpos + size_t(e) * (7 + md.nj), xpos, xquat, cinert, cdof, com, f);
+  for (int i = 0; i < 3 * md.nc; ++i) feet[size_t(e) * 3 * md.nc + i] = f[i];
+}
+
 }  // namespace
 
 extern "C" {
@@ -81,6 +97,7 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   if (!mdl) return MPXB_EINVAL;
   mdl->desc = *d;
   mdl->wb_dev = nullptr;
+  mdl->prof = nullptr;
   cudaGetDevice(&mdl->device);
   if (d->kind == MPXB_KIND_SRBD) {
     if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
@@ -150,6 +167,9 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
     LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost};
     TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi};
+    mpxb_profile* pf = (it == max_iter - 1 && mdl->prof && mdl->prof->calls < mdl->prof->max_calls) ? mdl->prof : nullptr;
+    cudaEvent_t* pev = pf ? pf->ev + 5 * pf->calls : nullptr;
+    if (pev) cudaEventRecord(pev[0], st);
     // K1
     if (d.kind == MPXB_KIND_SRBD) {
       const int wpb = 4;
@@ -159,12 +179,14 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
       int rc = wb_launch_linearize(mdl->wb_host, mdl->wb_dev, io, lo, st);
       if (rc != MPXB_OK) return rc;
     }
+    if (pev) cudaEventRecord(pev[1], st);
     // K2
     LqArgs la{E, N, ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c,
               ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done};
     int rc = (lq_mode == MPXB_LQ_SEQUENTIAL) ? dispatch_lq_seq(n, m, la, st)
                                              : dispatch_lq_scan(n, m, la, ws + L.scan, st);
     if (rc != MPXB_OK) return rc;
+    if (pev) cudaEventRecord(pev[2], st);
     // K3
     if (d.kind == MPXB_KIND_SRBD) {
       const int wpb = 4;
@@ -174,11 +196,13 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
       rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, io, to, st);
       if (rc != MPXB_OK) return rc;
     }
+    if (pev) cudaEventRecord(pev[3], st);
     // K4
     SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.cost, ws + L.c, ws + L.ls_theta,
                   ws + L.ls_phi, ws + L.slope, Xn, Un, Vn, ws + L.g, ws + L.last_cost, done, alpha_index, iters,
                   status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0};
     select_update_kernel<<<E, 128, 0, st>>>(sa);
+    if (pev) { cudaEventRecord(pev[4], st); pf->calls++; }
     Xc = Xn; Uc = Un; Vc = Vn;
   }
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
@@ -214,6 +238,64 @@ int mpxb_shift_extract(const mpxb_model* mdl, void* stream, int E, int shift, co
   shift_extract_kernel<<<E, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, d.N, d.n, d.m, d.n_joints, shift, wb, X, U,
                                                                          V, x0, u_ref, X0, U0, V0, tau, q, dq);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+int mpxb_wb_foot_positions(const mpxb_model* mdl, void* stream, int E, const float* qpos, float* feet) {
+  if (!mdl || !qpos || !feet || E <= 0) return MPXB_EINVAL;
+  if (mdl->desc.kind == MPXB_KIND_SRBD) return MPXB_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WbModel& h = mdl->wb_host;
+  const int nt = 64, nb = (E + nt - 1) / nt;
+  if (h.nbody <= 14 && h.nv <= 18 && h.nc <= 4) wb_feet_kernel<14, 18, 4><<<nb, nt, 0, st>>>(mdl->wb_dev, E, qpos, feet);
+  else if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) wb_feet_kernel<21, 25, 4><<<nb, nt, 0, st>>>(mdl->wb_dev, E, qpos, feet);
+  else wb_feet_kernel<32, 28, 8><<<nb, nt, 0, st>>>(mdl->wb_dev, E, qpos, feet);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+int mpxb_profile_create(int max_calls, mpxb_profile** out) {
+  if (!out || max_calls <= 0) return MPXB_EINVAL;
+  mpxb_profile* p = new (std::nothrow) mpxb_profile();
+  if (!p) return MPXB_EINVAL;
+  p->max_calls = max_calls;
+  p->calls = 0;
+  p->ev = new (std::nothrow) cudaEvent_t[size_t(5) * max_calls];
+  if (!p->ev) { delete p; return MPXB_EINVAL; }
+  for (int i = 0; i < 5 * max_calls; ++i)
+    if (cudaEventCreate(&p->ev[i]) != cudaSuccess) { delete[] p->ev; delete p; return MPXB_ECUDA; }
+  *out = p;
+  return MPXB_OK;
+}
+
+void mpxb_profile_destroy(mpxb_profile* p) {
+  if (!p) return;
+  for (int i = 0; i < 5 * p->max_calls; ++i) cudaEventDestroy(p->ev[i]);
+  delete[] p->ev;
+  delete p;
+}
+
+int mpxb_profile_attach(mpxb_model* mdl, mpxb_profile* p) {
+  if (!mdl) return MPXB_EINVAL;
+  mdl->prof = p;
+  if (p) p->calls = 0;
+  return MPXB_OK;
+}
+
+int mpxb_profile_read(mpxb_profile* p, double mean_ms[4], int* calls) {
+  if (!p || !mean_ms) return MPXB_EINVAL;
+  for (int k = 0; k < 4; ++k) mean_ms[k] = 0.0;
+  for (int c = 0; c < p->calls; ++c) {
+    cudaEvent_t* ev = p->ev + 5 * c;
+    if (cudaEventSynchronize(ev[4]) != cudaSuccess) return MPXB_ECUDA;
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) != cudaSuccess) return MPXB_ECUDA;
+      mean_ms[k] += ms;
+    }
+  }
+  if (p->calls > 0)
+    for (int k = 0; k < 4; ++k) mean_ms[k] /= p->calls;
+  if (calls) *calls = p->calls;
+  return MPXB_OK;
 }
 
 // Standalone LQ solve (tvlqr + rollout + dual_lqr, or the scan forms): the reference functions a13-a16 of SURVEY 8a.

@@ -1,11 +1,270 @@
-// wb_kernels.cuh -- whole-body (MuJoCo-style tree) model kernels.  STUB: filled in after the SRBD slice.
+// wb_kernels.cuh -- whole-body model kernels: fused evaluate + linearise + quadratise and the 11-alpha trial
+// evaluation of the filter line search.  Reference: optimizers.py:580-602 (model_evaluator), 150-173
+// (linearize / hessian_approx / lagrangian), 518-540 (trial points); models.py:39-217; objectives.py:77-450.
+//
+// Linearisation: one CTA per (environment, knot); thread d carries forward-mode direction d of [qpos | qvel | u]
+// through the whole dynamics (the foot / GRF tail of the state does not enter f, so those columns of A are
+// zero: models.py:61,95,109-115).  A second pass carries the cost gradient; the Gauss-Newton blocks follow from
+// the residual map (identity except the 3x4 quaternion-error Jacobian) and the penalty curvatures.
 #pragma once
 #include "../../include/mpxb.h"
 #include "srbd_kernels.cuh"
+#include "wb.cuh"
 
 namespace mpxb {
-struct WbModel { int nbody; };
-inline int wb_build_model(const mpxb_model_desc&, WbModel*) { return MPXB_EUNSUPPORTED; }
-inline int wb_launch_linearize(const WbModel&, const WbModel*, const ModelIO&, const LinOut&, cudaStream_t) { return MPXB_EUNSUPPORTED; }
-inline int wb_launch_trial(const WbModel&, const WbModel*, const ModelIO&, const TrialOut&, cudaStream_t) { return MPXB_EUNSUPPORTED; }
+
+// residual row(s) of state index j (objectives.py residual(): identity except the quaternion block)
+struct WbResMap {
+  int cnt, a[3];
+  float c[3];
+};
+__device__ __forceinline__ WbResMap wb_resmap_x(const WbModel& md, int j, const float* G, const float* contact) {
+  WbResMap r;
+  const int nj = md.nj, nf = 3 * md.nc;
+  r.cnt = 1; r.c[0] = 1.f;
+  if (j < 3) {
+    r.a[0] = j;
+  } else if (j < 7) {
+    r.cnt = 3;
+    for (int k = 0; k < 3; ++k) { r.a[k] = 3 + k; r.c[k] = G[k * 4 + j - 3]; }
+  } else if (j < 13 + 2 * nj) {
+    r.a[0] = j - 1;
+  } else if (j < 13 + 2 * nj + nf) {
+    r.a[0] = j - 1;
+    if (md.kind == MPXB_KIND_QUAD_WB && !md.swing_tracking) r.c[0] = contact[(j - 13 - 2 * nj) / 3];
+  } else {
+    r.a[0] = j - 1 + nj;  // GRF carried in the state (quadruped / H1)
+  }
+  return r;
+}
+
+template <int NB, int NV, int NC, int NT>
+__global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  constexpr int NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF;  // upper bounds of n, m for this tree size
+  __shared__ WbModel md;
+  __shared__ float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+  const int tid = threadIdx.x;
+  {
+    const int* src = reinterpret_cast<const int*>(mdp);
+    int* dst = reinterpret_cast<int*>(&md);
+    for (int i = tid; i < int(sizeof(WbModel) / 4); i += NT) dst[i] = src[i];
+  }
+  const int N = io.N;
+  const int e = blockIdx.x / (N + 1), t = blockIdx.x - e * (N + 1);
+  if (io.done && io.done[e]) return;
+  __syncthreads();
+  const int n = md.n, m = md.m, nj = md.nj, nv = md.nv, nc = md.nc;
+  const int ndyn = 7 + nj + nv, ndir = ndyn + m;
+  const bool term = (t == N);
+  const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
+  const float* Ut = io.U + (size_t(e) * N + t) * m;
+  const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+  const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
+  const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
+  const float* W = io.W + size_t(e) * io.w_stride;
+  for (int i = tid; i < n; i += NT) {
+    sx[i] = Xt[i];
+    svn[i] = term ? 0.f : Vt[n + i];
+    satv[i] = 0.f;
+  }
+  for (int i = tid; i < m; i += NT) { su[i] = term ? 0.f : Ut[i]; satv[n + i] = 0.f; }
+  __syncthreads();
+
+  // ---- dynamics: primal + one Jacobian column per thread
+  if (!term) {
+    float* A = o.A + (size_t(e) * N + t) * n * n;
+    float* B = o.B + (size_t(e) * N + t) * n * m;
+    if (tid < ndir) {
+      Dual x[NX], u[NU], xn[NX];
+      for (int i = 0; i < n; ++i) x[i] = Dual(sx[i], i == tid ? 1.f : 0.f);
+      for (int i = 0; i < m; ++i) u[i] = Dual(su[i], ndyn + i == tid ? 1.f : 0.f);
+      wb_dynamics<Dual, NB, NV, NC>(md, x, u, par, xn);
+      float atv = 0.f;
+      if (tid < ndyn) {
+        for (int i = 0; i < n; ++i) { A[i * n + tid] = xn[i].d; atv = fmaf(xn[i].d, svn[i], atv); }
+        satv[tid] = atv;
+      } else {
+        const int ju = tid - ndyn;
+        for (int i = 0; i < n; ++i) { B[i * m + ju] = xn[i].d; atv = fmaf(xn[i].d, svn[i], atv); }
+        satv[n + ju] = atv;
+      }
+      if (tid == 0) {
+        float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
+        const float* Xn = Xt + n;
+        for (int i = 0; i < n; ++i) c[i] = xn[i].v - Xn[i];
+      }
+    }
+    // the foot / GRF tail of the state does not enter the dynamics
+    const int ntail = n - ndyn;
+    for (int idx = tid; idx < n * ntail; idx += NT) {
+      const int i = idx / ntail, j = ndyn + idx - i * ntail;
+      A[i * n + j] = 0.f;
+    }
+  }
+  if (t == 0)
+    for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
+
+  // ---- cost value + gradient (forward mode, one direction per thread per pass)
+  for (int d = tid; d < n + m; d += NT) {
+    if (term && d >= n) break;
+    Dual x[NX], u[NU];
+    for (int i = 0; i < n; ++i) x[i] = Dual(sx[i], i == d ? 1.f : 0.f);
+    for (int i = 0; i < m; ++i) u[i] = Dual(su[i], n + i == d ? 1.f : 0.f);
+    const Dual cst = wb_cost<Dual, NJ, NC>(md, W, ref, x, u, term);
+    sgrad[d] = cst.d;
+    if (d == 0) o.cost[size_t(e) * (N + 1) + t] = cst.v;
+  }
+  if (tid < 4) {
+    Dual q[4], rs[3];
+    for (int i = 0; i < 4; ++i) q[i] = Dual(sx[3 + i], i == tid ? 1.f : 0.f);
+    quat_sub(q, ref + 3, rs);
+    for (int k = 0; k < 3; ++k) sG[k * 4 + tid] = rs[k].d;
+  }
+  __syncthreads();
+  // q_t = grad_x cost + A^T V_{t+1} - V_t ; r_t = grad_u cost + B^T V_{t+1}   (optimizers.py:111-120,165-169)
+  for (int i = tid; i < n; i += NT) o.q[(size_t(e) * (N + 1) + t) * n + i] = sgrad[i] + satv[i] - Vt[i];
+  if (!term)
+    for (int i = tid; i < m; i += NT) o.r[(size_t(e) * N + t) * m + i] = sgrad[n + i] + satv[n + i];
+
+  // ---- Gauss-Newton blocks Q = Jx^T W Jx (+ penalty curvature), R, M   (objectives.py:127-202, 252-323, 378-450)
+  const int nw = md.nw, nf = 3 * nc;
+  const float* contact = ref + 13 + nj + nf;
+  const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
+  float* Q = o.Q + (size_t(e) * (N + 1) + t) * n * n;
+  for (int idx = tid; idx < n * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    const WbResMap ri = wb_resmap_x(md, i, sG, contact), rj = wb_resmap_x(md, j, sG, contact);
+    float s = 0.f;
+    for (int a = 0; a < ri.cnt; ++a)
+      for (int b = 0; b < rj.cnt; ++b) s = fmaf(ri.c[a] * rj.c[b], W[ri.a[a] * nw + rj.a[b]], s);
+    if (md.kind == MPXB_KIND_QUAD_WB) {
+      const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
+      if (i >= g0 && j >= g0 && (i - g0) / 3 == (j - g0) / 3) {
+        // friction cone curvature: eps = 1e-1 here (objectives.py:167), clip +-1e6, masked by contact
+        const int c = (i - g0) / 3;
+        const float gx = sx[g0 + 3 * c], gy = sx[g0 + 3 * c + 1], gz = sx[g0 + 3 * c + 2];
+        const float sq = sqrtf(gy * gy + gx * gx + 1e-1f);
+        const float h = fminf(fmaxf(penalty_dd(0.5f * gz - sq, 0.1f, 5.f), -1e6f), 1e6f) * contact[c];
+        const float jf[3] = {-gx / sq, -gy / sq, 0.5f};
+        s = fmaf(h * jf[i - g0 - 3 * c], jf[j - g0 - 3 * c], s);
+      }
+      if (i == j && i >= v0 && i < v0 + nj) {
+        const float dq = sx[i];
+        s += fminf(fmaxf(penalty_dd(10.01f - dq, 0.1f, 5.f), -1e6f), 1e6f) +
+             fminf(fmaxf(penalty_dd(dq + 10.01f, 0.1f, 5.f), -1e6f), 1e6f);
+      }
+    }
+    Q[idx] = s;
+  }
+  if (!term) {
+    float* M = o.M + (size_t(e) * N + t) * n * m;
+    for (int idx = tid; idx < n * m; idx += NT) {
+      const int i = idx / m, j = idx - i * m;
+      const WbResMap ri = wb_resmap_x(md, i, sG, contact);
+      float s = 0.f;
+      for (int a = 0; a < ri.cnt; ++a) s = fmaf(ri.c[a], W[ri.a[a] * nw + ua0 + j], s);
+      M[idx] = s;
+    }
+    float* R = o.R + (size_t(e) * N + t) * m * m;
+    for (int idx = tid; idx < m * m; idx += NT) {
+      const int i = idx / m, j = idx - i * m;
+      float s = W[(ua0 + i) * nw + ua0 + j];
+      if (md.kind == MPXB_KIND_QUAD_WB && i == j && i < nj) {
+        const float tq = su[i];
+        s += fminf(fmaxf(penalty_dd(44.01f - tq, 1.f, 1.f), -1e6f), 1e6f) +
+             fminf(fmaxf(penalty_dd(tq + 44.01f, 1.f, 1.f), -1e6f), 1e6f);
+      }
+      R[idx] = s;
+    }
+  }
+}
+
+// one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
+template <int NB, int NV, int NC>
+__global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  constexpr int NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF;
+  __shared__ WbModel md;
+  {
+    const int* src = reinterpret_cast<const int*>(mdp);
+    int* dst = reinterpret_cast<int*>(&md);
+    for (int i = threadIdx.x; i < int(sizeof(WbModel) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int N = io.N;
+  if (warp >= io.E * NALPHA) return;
+  const int e = warp / NALPHA, ia = warp - e * NALPHA;
+  if (io.done && io.done[e]) return;
+  const int n = md.n, m = md.m;
+  const float alpha = exp2f(-float(ia));
+  const float* W = io.W + size_t(e) * io.w_stride;
+  float theta = 0.f, phi = 0.f;
+  for (int t = lane; t <= N; t += 32) {
+    const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
+    const float* dXt = o.dX + (size_t(e) * (N + 1) + t) * n;
+    const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
+    const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
+    float x[NX], u[NU];
+    for (int i = 0; i < n; ++i) x[i] = fmaf(alpha, dXt[i], Xt[i]);
+    if (t < N) {
+      const float* Ut = io.U + (size_t(e) * N + t) * m;
+      const float* dUt = o.dU + (size_t(e) * N + t) * m;
+      for (int i = 0; i < m; ++i) u[i] = fmaf(alpha, dUt[i], Ut[i]);
+    } else {
+      for (int i = 0; i < m; ++i) u[i] = 0.f;
+    }
+    phi += wb_cost<float, NJ, NC>(md, W, ref, x, u, t == N);
+    if (t < N) {
+      float xn[NX];
+      wb_dynamics<float, NB, NV, NC>(md, x, u, par, xn);
+      for (int i = 0; i < n; ++i) {
+        const float r = xn[i] - fmaf(alpha, dXt[n + i], Xt[n + i]);
+        theta = fmaf(r, r, theta);
+      }
+    }
+    if (t == 0) {
+      for (int i = 0; i < n; ++i) {
+        const float r = io.x0[size_t(e) * n + i] - x[i];
+        theta = fmaf(r, r, theta);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    theta += __shfl_xor_sync(0xffffffffu, theta, s);
+    phi += __shfl_xor_sync(0xffffffffu, phi, s);
+  }
+  if (lane == 0) {
+    o.ls_theta[e * NALPHA + ia] = theta;
+    o.ls_phi[e * NALPHA + ia] = phi;
+  }
+}
+
+template <int NB, int NV, int NC, int NT>
+inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
+  const int ndir = 7 + h.nj + h.nv + h.m;
+  if (ndir > NT) return MPXB_EUNSUPPORTED;
+  wb_linearize_kernel<NB, NV, NC, NT><<<io.E * (io.N + 1), NT, 0, st>>>(dev, io, lo);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+// tree-size classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u]
+inline int wb_launch_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
+  if (h.nbody <= 14 && h.nv <= 18 && h.nc <= 4) return wb_launch_linearize_t<14, 18, 4, 64>(h, dev, io, lo, st);
+  if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) return wb_launch_linearize_t<21, 25, 4, 96>(h, dev, io, lo, st);
+  return wb_launch_linearize_t<32, 28, 8, 128>(h, dev, io, lo, st);
+}
+
+inline int wb_launch_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
+  const int wpb = 2;
+  const int blocks = (io.E * NALPHA + wpb - 1) / wpb;
+  if (h.nbody <= 14 && h.nv <= 18 && h.nc <= 4) wb_trial_kernel<14, 18, 4><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+  else if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) wb_trial_kernel<21, 25, 4><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+  else wb_trial_kernel<32, 28, 8><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
 }  // namespace mpxb

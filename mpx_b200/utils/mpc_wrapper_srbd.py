@@ -59,6 +59,8 @@ class BatchedMPCControllerWrapper:
                                                           self.contact_time, 1 / self.mpc_frequency)
         reference, parameter, self.liftoff, foot_ref_dot = self._ref_gen(
             t_timer=self.contact_time.clone(), x=x0, foot=foot_op, input=input, contact=contact, liftoff=self.liftoff)
+        reference, parameter = reference.contiguous(), parameter.contiguous()
+        self.reference, self.parameter = reference, parameter
         self.foot_ref = parameter[:, 0, 4:]
         self.foot_ref_dot = foot_ref_dot[:, 0, :]
         X, U, V = self._solve(reference, parameter, self.W, x0, self.batch_X0, self.batch_U0, self.batch_V0)
