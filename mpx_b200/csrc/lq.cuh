@@ -87,6 +87,72 @@ __device__ __forceinline__ void load_padded(float* __restrict__ dst, int ld, int
   }
 }
 
+// Forward rollout + dual update + slope, shared by the sequential and the scan backward passes
+// (primal_tvlqr.py:484-498 / 523-549: the prefix composition of the affine maps evaluated left to right;
+// dual_tvlqr.py:19).  dx, dxn: [LN] shared scratch, du: [LM] shared scratch.
+template <int n, int m, int NT>
+__device__ __forceinline__ void lq_rollout_dual(const LqArgs& a, int e, int tid, float* dx, float* dxn, float* du) {
+  const int N = a.N;
+  const float* gA = a.A + size_t(e) * N * n * n;
+  const float* gB = a.B + size_t(e) * N * n * m;
+  const float* gq = a.q + size_t(e) * (N + 1) * n;
+  const float* gr = a.r + size_t(e) * N * m;
+  const float* gc = a.c + size_t(e) * (N + 1) * n;
+  const float* gK = a.K + size_t(e) * N * m * n;
+  const float* gk = a.k + size_t(e) * N * m;
+  const float* gP = a.P + size_t(e) * (N + 1) * n * n;
+  const float* gp = a.p + size_t(e) * (N + 1) * n;
+  float* gdX = a.dX + size_t(e) * (N + 1) * n;
+  float* gdU = a.dU + size_t(e) * N * m;
+  float* gdV = a.dV + size_t(e) * (N + 1) * n;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
+  for (int i = tid; i < n; i += NT) dx[i] = gc[i];
+  float slope_acc = 0.f;  // meaningful in warp 0 lanes
+  __syncthreads();
+  for (int t = 0; t <= N; ++t) {
+    // dV_t = P_t dx + p_t ; (t < N) du = K_t dx + k_t
+    for (int row = warp; row < n + (t < N ? m : 0); row += nwarp) {
+      const float* src = (row < n) ? gP + size_t(t) * n * n + size_t(row) * n : gK + size_t(t) * m * n + size_t(row - n) * n;
+      float s = 0.f;
+      for (int j = lane; j < n; j += 32) s = fmaf(src[j], dx[j], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        if (row < n) gdV[size_t(t) * n + row] = s + gp[size_t(t) * n + row];
+        else du[row - n] = s + gk[size_t(t) * m + row - n];
+      }
+    }
+    for (int i = tid; i < n; i += NT) gdX[size_t(t) * n + i] = dx[i];
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = lane; i < n; i += 32) slope_acc = fmaf(gq[size_t(t) * n + i], dx[i], slope_acc);
+      if (t < N)
+        for (int i = lane; i < m; i += 32) slope_acc = fmaf(gr[size_t(t) * m + i], du[i], slope_acc);
+    }
+    if (t == N) break;
+    for (int i = tid; i < m; i += NT) gdU[size_t(t) * m + i] = du[i];
+    // dx_next = A_t dx + B_t du + c_{t+1}
+    for (int row = warp; row < n; row += nwarp) {
+      const float* ar = gA + size_t(t) * n * n + size_t(row) * n;
+      const float* br = gB + size_t(t) * n * m + size_t(row) * m;
+      float s = 0.f;
+      for (int j = lane; j < n; j += 32) s = fmaf(ar[j], dx[j], s);
+      for (int j = lane; j < m; j += 32) s = fmaf(br[j], du[j], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) dxn[row] = s + gc[size_t(t + 1) * n + row];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) dx[i] = dxn[i];
+    __syncthreads();
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) slope_acc += __shfl_xor_sync(0xffffffffu, slope_acc, o);
+    if (lane == 0) a.slope[e] = slope_acc;
+  }
+}
+
 template <int n, int m, int NT>
 __global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
   using L = LqSmemLayout<n, m>;
@@ -260,58 +326,7 @@ __global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
   __syncthreads();
 
   // ---- forward rollout + dual (primal_tvlqr.py:484-498, dual_tvlqr.py:19) ----
-  float* dx = sw;   // [LN]
-  float* dxn = sq;  // [LN]
-  float* du = sh;   // [LM]
-  float* gdX = a.dX + size_t(e) * (N + 1) * n;
-  float* gdU = a.dU + size_t(e) * N * m;
-  float* gdV = a.dV + size_t(e) * (N + 1) * n;
-  const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
-  for (int i = tid; i < n; i += NT) dx[i] = gc[i];
-  float slope_acc = 0.f;  // meaningful in warp 0 lanes
-  __syncthreads();
-  for (int t = 0; t <= N; ++t) {
-    // dV_t = P_t dx + p_t ; (t < N) du = K_t dx + k_t
-    for (int row = warp; row < n + (t < N ? m : 0); row += nwarp) {
-      const float* src = (row < n) ? gP + size_t(t) * n * n + size_t(row) * n : gK + size_t(t) * m * n + size_t(row - n) * n;
-      float s = 0.f;
-      for (int j = lane; j < n; j += 32) s = fmaf(src[j], dx[j], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) {
-        if (row < n) gdV[size_t(t) * n + row] = s + gp[size_t(t) * n + row];
-        else du[row - n] = s + gk[size_t(t) * m + row - n];
-      }
-    }
-    for (int i = tid; i < n; i += NT) gdX[size_t(t) * n + i] = dx[i];
-    __syncthreads();
-    if (warp == 0) {
-      for (int i = lane; i < n; i += 32) slope_acc = fmaf(gq[size_t(t) * n + i], dx[i], slope_acc);
-      if (t < N)
-        for (int i = lane; i < m; i += 32) slope_acc = fmaf(gr[size_t(t) * m + i], du[i], slope_acc);
-    }
-    if (t == N) break;
-    for (int i = tid; i < m; i += NT) gdU[size_t(t) * m + i] = du[i];
-    // dx_next = A_t dx + B_t du + c_{t+1}
-    for (int row = warp; row < n; row += nwarp) {
-      const float* ar = gA + size_t(t) * n * n + size_t(row) * n;
-      const float* br = gB + size_t(t) * n * m + size_t(row) * m;
-      float s = 0.f;
-      for (int j = lane; j < n; j += 32) s = fmaf(ar[j], dx[j], s);
-      for (int j = lane; j < m; j += 32) s = fmaf(br[j], du[j], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) dxn[row] = s + gc[size_t(t + 1) * n + row];
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += NT) dx[i] = dxn[i];
-    __syncthreads();
-  }
-  if (warp == 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) slope_acc += __shfl_xor_sync(0xffffffffu, slope_acc, o);
-    if (lane == 0) a.slope[e] = slope_acc;
-  }
+  lq_rollout_dual<n, m, NT>(a, e, tid, sw, sq, sh);
 }
 
 }  // namespace mpxb
