@@ -32,6 +32,8 @@ struct WbModel {
   int contact_body[WB_MAXC];
   float contact_pos[WB_MAXC][3];
   uint32_t contact_dofmask[WB_MAXC];  // dofs whose body is the contact body or one of its ancestors
+  int depth[WB_MAXB];                 // base = 0 (bodies are numbered depth-first, parents before children)
+  int maxdepth;
 };
 
 // mpxb_model_desc (host, include/mpxb.h) -> WbModel: derived dof tables and contact ancestor masks
@@ -67,6 +69,9 @@ inline int wb_build_model(const mpxb_model_desc& d, WbModel* o) {
     for (int i = 0; i < 4; ++i) { w.body_quat[b][i] = d.body_quat[b][i]; w.iquat[b][i] = d.body_iquat[b][i]; }
     w.mass[b] = d.body_mass[b];
     w.qpos0[b] = d.jnt_qpos0[b];
+    w.depth[b] = (b <= 1) ? 0 : w.depth[w.parent[b]] + 1;
+    if (b > 1 && w.parent[b] < 1) return MPXB_EUNSUPPORTED;  // a single tree hanging off the floating base
+    if (w.depth[b] + 1 > w.maxdepth) w.maxdepth = w.depth[b] + 1;
     const int pl = (b == 0) ? -1 : lastdof[w.parent[b]];
     if (w.jtype[b] == WB_JNT_FREE) {
       if (b != 1 || w.dofadr[b] != 0) return MPXB_EUNSUPPORTED;  // one floating base, first in the tree
@@ -482,6 +487,469 @@ HD T wb_cost(const WbModel& md, const float* W, const float* ref, const T* x, co
     }
   }
   return 0.5f * cost;
+}
+
+}  // namespace mpxb
+
+// ====================================================================================================
+// Single-pass depth-first evaluation of the tree quantities with a path stack (v2 of the linearisation).
+//
+// The bodies are visited in index order (depth-first pre-order); slot d of the stack holds the current ancestor
+// at depth d: pose, joint motion axis, spatial velocity / bias acceleration, and the composite inertia / force
+// accumulated from its finished descendants.  Mass-matrix entries, bias forces, foot positions and foot
+// Jacobians are handed to a `sink` the moment they are final, so a forward-mode (Dual) pass can fold their
+// tangents into a handful of matrix-vector products without ever storing dM/dJ per direction.
+// Reference point of all spatial quantities: the base position qpos[0:3] (mjx uses the subtree COM; qM,
+// qfrc_bias, the contact Jacobians and geom_xpos do not depend on that choice).
+namespace mpxb {
+
+constexpr int WB_SLOT = 41;
+enum { WS_POS = 0, WS_QUAT = 3, WS_CDOF = 7, WS_CVEL = 13, WS_CACC = 19, WS_CRB = 25, WS_CFRC = 35 };
+
+template <class T> struct WbStackPlain {  // host / single-thread storage
+  T* p;
+  HD T ld(int i) const { return p[i]; }
+  HD void st(int i, T v) const { p[i] = v; }
+};
+
+// cdof of dof j, which lives on the body in stack slot sd
+template <class T, class Stk>
+HD void wb_slot_cdof(const WbModel& md, const Stk& stk, int sd, int sb, int j, const T* Rb, T* cd) {
+  if (md.jtype[sb] == WB_JNT_FREE) {
+    const int k = j - md.dofadr[sb];
+    for (int i = 0; i < 3; ++i) {
+      cd[i] = (k < 3) ? T(0.f) : Rb[3 * i + (k - 3)];
+      cd[3 + i] = T((k < 3 && i == k) ? 1.f : 0.f);
+    }
+  } else {
+    for (int i = 0; i < 6; ++i) cd[i] = stk.ld(sd * WB_SLOT + WS_CDOF + i);
+  }
+}
+
+template <class T, class Stk, class Sink>
+HD void wb_dfs_finish(const WbModel& md, const Stk& stk, const int* slot_body, int dd, const T* Rb, Sink& sink) {
+  const int b = slot_body[dd];
+  T crb[10], cfrc[6];
+  for (int i = 0; i < 10; ++i) crb[i] = stk.ld(dd * WB_SLOT + WS_CRB + i);
+  for (int i = 0; i < 6; ++i) cfrc[i] = stk.ld(dd * WB_SLOT + WS_CFRC + i);
+  const int jt = md.jtype[b];
+  const int nd = (jt == WB_JNT_FREE) ? 6 : (jt == WB_JNT_HINGE ? 1 : 0);
+  for (int a = nd - 1; a >= 0; --a) {
+    const int i = md.dofadr[b] + a;
+    T cdi[6], f[6];
+    wb_slot_cdof(md, stk, dd, b, i, Rb, cdi);
+    inert_mul(crb, cdi, f);
+    T bs = cdi[0] * cfrc[0];
+    for (int k = 1; k < 6; ++k) bs = bs + cdi[k] * cfrc[k];
+    sink.bias(i, bs);
+    for (int sd = dd; sd >= 0; --sd) {
+      const int sb = slot_body[sd];
+      const int jts = md.jtype[sb];
+      if (jts != WB_JNT_FREE && jts != WB_JNT_HINGE) continue;
+      const int j0 = md.dofadr[sb];
+      const int jhi = (jts == WB_JNT_FREE) ? ((sd == dd) ? i : j0 + 5) : j0;
+      for (int j = jhi; j >= j0; --j) {
+        T cdj[6];
+        if (j == i) { for (int k = 0; k < 6; ++k) cdj[k] = cdi[k]; }
+        else wb_slot_cdof(md, stk, sd, sb, j, Rb, cdj);
+        T mij = f[0] * cdj[0];
+        for (int k = 1; k < 6; ++k) mij = mij + f[k] * cdj[k];
+        if (j == i) mij = mij + md.armature[i];
+        sink.mass(i, j, mij);
+      }
+    }
+  }
+  if (dd > 0) {
+    const int pd = dd - 1;
+    for (int i = 0; i < 10; ++i) stk.st(pd * WB_SLOT + WS_CRB + i, stk.ld(pd * WB_SLOT + WS_CRB + i) + crb[i]);
+    for (int i = 0; i < 6; ++i) stk.st(pd * WB_SLOT + WS_CFRC + i, stk.ld(pd * WB_SLOT + WS_CFRC + i) + cfrc[i]);
+  }
+}
+
+// TV: scalar type of the velocity-dependent quantities (== T, or float with T = float)
+template <class T> struct WbInPlain {  // (qpos, qvel) from plain arrays
+  const T* qp; const T* qv;
+  HD T q(int i) const { return qp[i]; }
+  HD T v(int i) const { return qv[i]; }
+};
+struct WbInSeed {  // forward-mode seed on entry `dir` of x = [qpos | qvel | ...]
+  const float* x; int nq, dir;
+  HD Dual q(int i) const { return Dual(x[i], i == dir ? 1.f : 0.f); }
+  HD Dual v(int i) const { return Dual(x[nq + i], nq + i == dir ? 1.f : 0.f); }
+};
+
+template <class T, class In, class Stk, class Sink>
+HD void wb_dfs(const WbModel& md, const In& in, const Stk& stk, Sink& sink) {
+  int slot_body[WB_MAXB];
+  T Rb[9];
+  const T ref[3] = {in.q(0), in.q(1), in.q(2)};
+  int cur = -1;
+  const int nb = md.nbody;
+  for (int b = 1; b < nb; ++b) {
+    const int d = md.depth[b];
+    for (int dd = cur; dd >= d; --dd) wb_dfs_finish(md, stk, slot_body, dd, Rb, sink);
+    cur = d;
+    slot_body[d] = b;
+    const int so = d * WB_SLOT;
+    T pos[3], quat[4], cdof[6], cv[6], ca[6];
+    const int jt = md.jtype[b];
+    if (d == 0) {
+      for (int i = 0; i < 3; ++i) pos[i] = ref[i];
+      {
+        const T q4[4] = {in.q(3), in.q(4), in.q(5), in.q(6)};
+        normalize_with_norm<T, 4>(q4, quat);
+      }
+      quat_to_mat(quat, Rb);
+      // mjx com_vel for the free joint: translation first, angular cdof_dot against the translated velocity
+      for (int i = 0; i < 3; ++i) { cv[i] = T(0.f); cv[3 + i] = in.v(i); ca[i] = T(0.f); ca[3 + i] = T(-md.gravity[i]); }
+      T cd[3][6];
+      for (int a = 0; a < 3; ++a) {
+        T cdr[6] = {Rb[a], Rb[3 + a], Rb[6 + a], T(0.f), T(0.f), T(0.f)};
+        motion_cross(cv, cdr, cd[a]);
+      }
+      for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 6; ++k) {
+          if (k < 3) cv[k] = cv[k] + Rb[3 * k + a] * in.v(3 + a);
+          ca[k] = ca[k] + cd[a][k] * in.v(3 + a);
+        }
+      for (int i = 0; i < 6; ++i) cdof[i] = T(0.f);
+    } else {
+      T ppos[3], pquat[4], r[3];
+      for (int i = 0; i < 3; ++i) ppos[i] = stk.ld(so - WB_SLOT + WS_POS + i);
+      for (int i = 0; i < 4; ++i) pquat[i] = stk.ld(so - WB_SLOT + WS_QUAT + i);
+      for (int i = 0; i < 6; ++i) { cv[i] = stk.ld(so - WB_SLOT + WS_CVEL + i); ca[i] = stk.ld(so - WB_SLOT + WS_CACC + i); }
+      quat_rotate(pquat, md.body_pos[b], r);
+      for (int i = 0; i < 3; ++i) pos[i] = ppos[i] + r[i];
+      quat_mul(pquat, md.body_quat[b], quat);
+      if (jt == WB_JNT_HINGE) {
+        const int dj = md.dofadr[b];
+        T anchor[3], axis[3], o[3], l[3];
+        quat_rotate(quat, md.jnt_pos[b], r);
+        for (int i = 0; i < 3; ++i) anchor[i] = r[i] + pos[i];
+        quat_rotate(quat, md.jnt_axis[b], axis);
+        const T half = (in.q(dj + 1) - md.qpos0[b]) * 0.5f;
+        const T sn = xsin(half), cs = xcos(half);
+        T qloc[4] = {cs, md.jnt_axis[b][0] * sn, md.jnt_axis[b][1] * sn, md.jnt_axis[b][2] * sn};
+        T q2[4];
+        quat_mul(quat, qloc, q2);
+        for (int i = 0; i < 4; ++i) quat[i] = q2[i];
+        quat_rotate(quat, md.jnt_pos[b], r);
+        for (int i = 0; i < 3; ++i) { pos[i] = anchor[i] - r[i]; o[i] = ref[i] - anchor[i]; }
+        cross3(axis, o, l);
+        for (int i = 0; i < 3; ++i) { cdof[i] = axis[i]; cdof[3 + i] = l[i]; }
+        T cd[6];
+        motion_cross(cv, cdof, cd);
+        const T qd = in.v(dj);
+        for (int k = 0; k < 6; ++k) { ca[k] = ca[k] + cd[k] * qd; cv[k] = cv[k] + cdof[k] * qd; }
+      } else {
+        for (int i = 0; i < 6; ++i) cdof[i] = T(0.f);
+      }
+    }
+    for (int i = 0; i < 3; ++i) stk.st(so + WS_POS + i, pos[i]);
+    for (int i = 0; i < 4; ++i) stk.st(so + WS_QUAT + i, quat[i]);
+    for (int i = 0; i < 6; ++i) { stk.st(so + WS_CDOF + i, cdof[i]); stk.st(so + WS_CVEL + i, cv[i]); stk.st(so + WS_CACC + i, ca[i]); }
+    // spatial inertia about the reference point, local force
+    {
+      T r[3], off[3], qi[4], R[9], ci[10];
+      quat_rotate(quat, md.ipos[b], r);
+      for (int i = 0; i < 3; ++i) off[i] = pos[i] + r[i] - ref[i];
+      quat_mul(quat, md.iquat[b], qi);
+      quat_to_mat(qi, R);
+      const float mb = md.mass[b];
+      const float* I = md.inertia[b];
+      const T o2 = off[0] * off[0] + off[1] * off[1] + off[2] * off[2];
+      const int ia[6] = {0, 1, 2, 0, 0, 1}, ib[6] = {0, 1, 2, 1, 2, 2};
+      for (int k = 0; k < 6; ++k) {
+        const int a = ia[k], c = ib[k];
+        T v = R[3 * a] * (R[3 * c] * I[0]) + R[3 * a + 1] * (R[3 * c + 1] * I[1]) + R[3 * a + 2] * (R[3 * c + 2] * I[2]);
+        v = v - off[a] * off[c] * mb;
+        if (a == c) v = v + o2 * mb;
+        ci[k] = v;
+      }
+      for (int i = 0; i < 3; ++i) ci[6 + i] = off[i] * mb;
+      ci[9] = T(mb);
+      T f1[6], f2[6], f3[6];
+      inert_mul(ci, ca, f1);
+      inert_mul(ci, cv, f2);
+      motion_cross_force(cv, f2, f3);
+      for (int i = 0; i < 10; ++i) stk.st(so + WS_CRB + i, ci[i]);
+      for (int i = 0; i < 6; ++i) stk.st(so + WS_CFRC + i, f1[i] + f3[i]);
+    }
+    // contact points carried by this body: position and translational Jacobian over the path
+    for (int c = 0; c < md.nc; ++c) {
+      if (md.contact_body[c] != b) continue;
+      T r[3], foot[3], off[3];
+      quat_rotate(quat, md.contact_pos[c], r);
+      for (int i = 0; i < 3; ++i) { foot[i] = pos[i] + r[i]; off[i] = foot[i] - ref[i]; }
+      sink.foot(c, foot);
+      for (int sd = d; sd >= 0; --sd) {
+        const int sb = slot_body[sd];
+        const int jts = md.jtype[sb];
+        if (jts != WB_JNT_FREE && jts != WB_JNT_HINGE) continue;
+        const int j0 = md.dofadr[sb], j1 = j0 + (jts == WB_JNT_FREE ? 5 : 0);
+        for (int j = j1; j >= j0; --j) {
+          T cdj[6], cr[3], jc[3];
+          if (sd == d && jts == WB_JNT_HINGE) { for (int k = 0; k < 6; ++k) cdj[k] = cdof[k]; }
+          else wb_slot_cdof(md, stk, sd, sb, j, Rb, cdj);
+          cross3(cdj, off, cr);
+          for (int i = 0; i < 3; ++i) jc[i] = cdj[3 + i] + cr[i];
+          sink.jac(j, c, jc);
+        }
+      }
+    }
+  }
+  for (int dd = cur; dd >= 0; --dd) wb_dfs_finish(md, stk, slot_body, dd, Rb, sink);
+}
+
+// Sink that stores the primal terms: M [nv][ldm] (full symmetric; entries off the tree paths must be pre-zeroed),
+// bias [nv], J [nv][ldj] (pre-zeroed), feet [3 nc].
+template <class T> struct WbStoreSink {
+  T* Mp; int ldm; T* biasp; T* Jp; int ldj; T* feetp;
+  HD void mass(int i, int j, T v) { Mp[i * ldm + j] = v; Mp[j * ldm + i] = v; }
+  HD void bias(int i, T v) { biasp[i] = v; }
+  HD void foot(int c, const T* p) { for (int k = 0; k < 3; ++k) feetp[3 * c + k] = p[k]; }
+  HD void jac(int j, int c, const T* v) { for (int k = 0; k < 3; ++k) Jp[j * ldj + 3 * c + k] = v[k]; }
+};
+
+// Forward-mode sink: folds the tangents of the mass matrix / bias force / foot Jacobian entries of ONE direction
+// into the matrix-vector products the analytic contact-solve derivative needs (see wb_s3_tangent):
+//   t1 = -dD - dM w          t2 = -dD - dM a + dJ grf          e = dJ y - dM z          h = dJ' (w + 2 alpha qvel + z)
+struct WbTangentSink {
+  float *t1, *t2, *e, *h, *dfeet;                     // per-direction accumulators (pre-zeroed)
+  const float *w, *z, *a, *y, *grf, *wvz;             // primal vectors of the knot
+  HD void mass(int i, int j, Dual v) {
+    const float d = v.d;
+    t1[i] -= d * w[j]; t2[i] -= d * a[j]; e[i] -= d * z[j];
+    if (i != j) { t1[j] -= d * w[i]; t2[j] -= d * a[i]; e[j] -= d * z[i]; }
+  }
+  HD void bias(int i, Dual v) { t1[i] -= v.d; t2[i] -= v.d; }
+  HD void foot(int c, const Dual* p) { for (int k = 0; k < 3; ++k) dfeet[3 * c + k] = p[k].d; }
+  HD void jac(int j, int c, const Dual* v) {
+    for (int k = 0; k < 3; ++k) {
+      const float d = v[k].d;
+      const int col = 3 * c + k;
+      e[j] += d * y[col]; t2[j] += d * grf[col]; h[col] += d * wvz[j];
+    }
+  }
+};
+
+// x <- (L L')^-1 x with the strictly-lower part of L in Lm (ld) and its diagonal in dL; K is the exact size so the
+// loops unroll and x stays in registers
+template <int K> HD void wb_tri_solve(const float* Lm, int ld, const float* dL, float* x) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    float s = x[i];
+#pragma unroll
+    for (int p = 0; p < i; ++p) s = fmaf(-Lm[i * ld + p], x[p], s);
+    x[i] = s / dL[i];
+  }
+#pragma unroll
+  for (int i = K - 1; i >= 0; --i) {
+    float s = x[i];
+#pragma unroll
+    for (int p = i + 1; p < K; ++p) s = fmaf(-Lm[p * ld + i], x[p], s);
+    x[i] = s / dL[i];
+  }
+}
+
+// Per-knot primal workspace of the analytic contact solve (shared memory in the kernel)
+template <int NV, int NC> struct WbKnot {
+  static constexpr int NF = 3 * NC, NX = 13 + 2 * (NV - 6) + 2 * NF;
+  float M[NV * NV];      // qM -> strictly-lower Cholesky factor in place (diagonal in dL)
+  float J[NV * NF], MiJ[NV * NF], JMJ[NF * NF];
+  float dL[NV], dLc[NF], D[NV], tmd[NV], w[NV], a[NV], z[NV], wvz[NV];
+  float y[NF], grf[NF], feet[NF];
+  float xn[NX], Gq[16], Gw[12];
+};
+
+// Cooperative primal contact solve (models.py:93-115 / 146-167 / 206-215): `lane` of `nl` workers, `sync()` between
+// the dependent steps.  Host: lane 0 of 1 with a no-op sync.
+template <int NV, int NC, class Sync>
+HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u, const float* contact, int lane,
+                     int nl, Sync sync) {
+  constexpr int NF = 3 * NC;
+  const int nv = md.nv, nj = md.nj, nf = 3 * md.nc;
+  const float* qvel = x + 7 + nj;
+  for (int i = lane; i < nv; i += nl) k.tmd[i] = (i < 6 ? 0.f : u[i - 6]) - k.D[i];
+  for (int idx = lane; idx < nv * NF; idx += nl) k.MiJ[idx] = k.J[idx];
+  sync();
+  // Cholesky of qM, one column per step; every worker recomputes the pivot so a single barrier per column suffices
+  for (int j = 0; j < nv; ++j) {
+    float sjj = k.M[j * NV + j];
+    for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
+    const float dj = sqrtf(sjj);
+    for (int i = j + 1 + lane; i < nv; i += nl) {
+      float s = k.M[i * NV + j];
+      for (int p = 0; p < j; ++p) s = fmaf(-k.M[i * NV + p], k.M[j * NV + p], s);
+      k.M[i * NV + j] = s / dj;
+    }
+    if (lane == 0) k.dL[j] = dj;
+    sync();
+  }
+  if (md.contact_solve) {
+    for (int c = lane; c <= nf; c += nl) {
+      if (c < nf) {
+        float col[NV];
+        for (int i = 0; i < nv; ++i) col[i] = k.MiJ[i * NF + c];
+        wb_tri_solve<NV>(k.M, NV, k.dL, col);
+        for (int i = 0; i < nv; ++i) k.MiJ[i * NF + c] = col[i];
+      } else {
+        float col[NV];
+        for (int i = 0; i < nv; ++i) col[i] = k.tmd[i];
+        wb_tri_solve<NV>(k.M, NV, k.dL, col);
+        for (int i = 0; i < nv; ++i) k.w[i] = col[i];
+      }
+    }
+    sync();
+    for (int idx = lane; idx < nf * nf + nf; idx += nl) {
+      if (idx < nf * nf) {
+        const int a = idx / nf, b = idx - a * nf;
+        if (b <= a) {
+          float s = 0.f;
+          for (int i = 0; i < nv; ++i) s = fmaf(k.J[i * NF + a], k.MiJ[i * NF + b], s);
+          if (a == b) s += md.reg;
+          k.JMJ[a * NF + b] = s;
+        }
+      } else {
+        const int a = idx - nf * nf;
+        float s = 0.f;
+        for (int i = 0; i < nv; ++i) s = fmaf(k.J[i * NF + a], k.w[i] + 2.f * md.alpha * qvel[i], s);
+        k.y[a] = -s;
+      }
+    }
+    sync();
+    for (int j = 0; j < nf; ++j) {
+      float sjj = k.JMJ[j * NF + j];
+      for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
+      const float dj = sqrtf(sjj);
+      for (int i = j + 1 + lane; i < nf; i += nl) {
+        float s = k.JMJ[i * NF + j];
+        for (int p = 0; p < j; ++p) s = fmaf(-k.JMJ[i * NF + p], k.JMJ[j * NF + p], s);
+        k.JMJ[i * NF + j] = s / dj;
+      }
+      if (lane == 0) k.dLc[j] = dj;
+      sync();
+    }
+    if (lane == 0) { float yy[NF]; for (int c = 0; c < NF; ++c) yy[c] = k.y[c]; wb_tri_solve<NF>(k.JMJ, NF, k.dLc, yy); for (int c = 0; c < NF; ++c) k.y[c] = yy[c]; }
+    sync();
+    for (int c = lane; c < nf; c += nl) k.grf[c] = k.y[c] * contact[c / 3];
+    sync();
+    for (int i = lane; i < nv; i += nl) {
+      float sz = 0.f, sa = k.w[i];
+      for (int c = 0; c < nf; ++c) { sz = fmaf(k.MiJ[i * NF + c], k.y[c], sz); sa = fmaf(k.MiJ[i * NF + c], k.grf[c], sa); }
+      k.z[i] = sz;
+      k.a[i] = sa;
+      k.wvz[i] = k.w[i] + 2.f * md.alpha * qvel[i] + sz;
+    }
+  } else {
+    for (int c = lane; c < nf; c += nl) { k.grf[c] = u[nj + c] * contact[c / 3]; k.y[c] = 0.f; }
+    for (int i = lane; i < nv; i += nl) { k.w[i] = 0.f; k.z[i] = 0.f; k.wvz[i] = 0.f; }
+    sync();
+    if (lane == 0) {
+      float col[NV];
+      for (int i = 0; i < nv; ++i) {
+        float s = k.tmd[i];
+        for (int c = 0; c < nf; ++c) s = fmaf(k.J[i * NF + c], k.grf[c], s);
+        col[i] = s;
+      }
+      wb_tri_solve<NV>(k.M, NV, k.dL, col);
+      for (int i = 0; i < nv; ++i) k.a[i] = col[i];
+    }
+  }
+  sync();
+  // semi-implicit Euler step and the Jacobians of quat_integrate wrt (quat, omega+)
+  const float dt = md.dt;
+  float* vn = k.xn + 7 + nj;
+  for (int i = lane; i < nv; i += nl) vn[i] = qvel[i] + k.a[i] * dt;
+  sync();
+  for (int i = lane; i < 3; i += nl) k.xn[i] = x[i] + vn[i] * dt;
+  for (int i = lane; i < nj; i += nl) k.xn[7 + i] = x[7 + i] + vn[6 + i] * dt;
+  for (int i = lane; i < nf; i += nl) {
+    k.xn[7 + nj + nv + i] = k.feet[i];
+    if (md.grf_as_state) k.xn[7 + nj + nv + nf + i] = k.grf[i];
+  }
+  for (int s = lane; s < 8; s += nl) {
+    if (s < 7) {
+      Dual q[4], om[3], qo[4];
+      for (int i = 0; i < 4; ++i) q[i] = Dual(x[3 + i], s == i ? 1.f : 0.f);
+      for (int i = 0; i < 3; ++i) om[i] = Dual(vn[3 + i], s == 4 + i ? 1.f : 0.f);
+      quat_integrate(q, om, dt, qo);
+      for (int r = 0; r < 4; ++r) {
+        if (s < 4) k.Gq[r * 4 + s] = qo[r].d;
+        else k.Gw[r * 3 + s - 4] = qo[r].d;
+      }
+    } else {
+      float qo[4];
+      quat_integrate(x + 3, vn + 3, dt, qo);
+      for (int r = 0; r < 4; ++r) k.xn[3 + r] = qo[r];
+    }
+  }
+  sync();
+}
+
+// One column of [A | B] from the folded tangents of one direction (see WbTangentSink), handed entry by entry to
+// out(i, value), i = 0..n-1 in increasing order.
+//   is_u == 0: state direction `dir` in [0, 7+nj+nv) ; is_u == 1: control direction `dir` in [0, m).
+// t1, t2, e, h, dfeet are the direction's accumulators (ignored for a control direction).  Requires nv == NV, nc == NC.
+template <int NV, int NC, class Out>
+HD void wb_s3_tangent(const WbModel& md, const WbKnot<NV, NC>& k, const float* contact, int is_u, int dir, const float* t1,
+                      const float* t2, const float* e, const float* h, const float* dfeet, Out out) {
+  constexpr int NF = 3 * NC, NJ = NV - 6, NQ = NV + 1;
+  float dgrf[NF], xa[NV];
+  const int kv = (!is_u && dir >= NQ) ? dir - NQ : -1;  // velocity direction index
+  if (md.contact_solve) {
+    float xw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xw[i] = is_u ? ((i == 6 + dir) ? 1.f : 0.f) : t1[i];
+    wb_tri_solve<NV>(k.M, NV, k.dL, xw);  // dw
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      float s = is_u ? 0.f : -h[c];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s = fmaf(-k.J[i * NF + c], xw[i], s);
+      if (!is_u) {
+        for (int i = 0; i < NV; ++i) s = fmaf(-k.MiJ[i * NF + c], e[i], s);
+        if (kv >= 0) s = fmaf(-2.f * md.alpha, k.J[kv * NF + c], s);
+      }
+      dgrf[c] = s;
+    }
+    wb_tri_solve<NF>(k.JMJ, NF, k.dLc, dgrf);
+#pragma unroll
+    for (int c = 0; c < NF; ++c) dgrf[c] *= contact[c / 3];
+  } else {
+#pragma unroll
+    for (int c = 0; c < NF; ++c) dgrf[c] = (is_u && dir == NJ + c) ? contact[c / 3] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float s = is_u ? ((i == 6 + dir && dir < NJ) ? 1.f : 0.f) : t2[i];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) s = fmaf(k.J[i * NF + c], dgrf[c], s);
+    xa[i] = s;
+  }
+  wb_tri_solve<NV>(k.M, NV, k.dL, xa);  // da
+  const float dt = md.dt;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xa[i] = ((i == kv) ? 1.f : 0.f) + dt * xa[i];  // d v+
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out(i, ((!is_u && dir == i) ? 1.f : 0.f) + dt * xa[i]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float s = (!is_u && dir >= 3 && dir < 7) ? k.Gq[r * 4 + dir - 3] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s = fmaf(k.Gw[r * 3 + c], xa[3 + c], s);
+    out(3 + r, s);
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) out(7 + i, ((!is_u && dir == 7 + i) ? 1.f : 0.f) + dt * xa[6 + i]);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out(NQ + i, xa[i]);
+#pragma unroll
+  for (int c = 0; c < NF; ++c) out(NQ + NV + c, is_u ? 0.f : dfeet[c]);
+  if (md.grf_as_state) {
+#pragma unroll
+    for (int c = 0; c < NF; ++c) out(NQ + NV + NF + c, dgrf[c]);
+  }
 }
 
 }  // namespace mpxb

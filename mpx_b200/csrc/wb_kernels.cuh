@@ -38,24 +38,42 @@ __device__ __forceinline__ WbResMap wb_resmap_x(const WbModel& md, int j, const 
   return r;
 }
 
-template <int NB, int NV, int NC, int NT>
+// Forward-mode path stack of the linearise kernel: the primal half is identical in every lane and lives once per
+// warp, the tangent half is private to the lane (direction) and lane-interleaved in shared memory.
+struct WbStackSplit {
+  float* prim;
+  float* tan;
+  int stride;
+  __device__ __forceinline__ Dual ld(int i) const { return Dual(prim[i], tan[i * stride]); }
+  __device__ __forceinline__ void st(int i, Dual v) const { prim[i] = v.v; tan[i * stride] = v.d; }
+};
+
+template <int NV, int NC, int MAXD, int NT> struct WbLinSmem {
+  static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
+  WbKnot<NV, NC> k;
+  float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+  float prim[NT / 32][MAXD * WB_SLOT];
+  float tan[MAXD * WB_SLOT * NDS];
+};
+
+// One CTA per (environment, knot).  Phases (DESIGN.md "linearise kernel"):
+//   P1  thread 0: primal path-stack pass  -> qM, qfrc_bias, J, feet in shared memory
+//   P2  all threads: cooperative contact solve (Cholesky of qM, M^-1 J, J'M^-1J, GRFs, x+)
+//   P3  thread d < nq+nv: forward-mode path-stack pass of state direction d, tangents folded by WbTangentSink
+//   P4  thread d < nq+nv+m: analytic contact-solve derivative -> column d of [A | B], A'V / B'V
+//   P5  all threads: cost gradient (forward mode), q, r, Gauss-Newton Q, R, M
+template <int NV, int NC, int MAXD, int NT>
 __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
-  constexpr int NJ = NV - 6, NF = 3 * NC;
-  constexpr int NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF;  // upper bounds of n, m for this tree size
-  __shared__ WbModel md;
-  __shared__ float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+  using S = WbLinSmem<NV, NC, MAXD, NT>;
+  constexpr int NJ = S::NJ, NF = S::NF, NX = S::NX, NU = S::NU, NDS = S::NDS, NQ = NV + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const WbModel& md = *mdp;
   const int tid = threadIdx.x;
-  {
-    const int* src = reinterpret_cast<const int*>(mdp);
-    int* dst = reinterpret_cast<int*>(&md);
-    for (int i = tid; i < int(sizeof(WbModel) / 4); i += NT) dst[i] = src[i];
-  }
   const int N = io.N;
   const int e = blockIdx.x / (N + 1), t = blockIdx.x - e * (N + 1);
   if (io.done && io.done[e]) return;
-  __syncthreads();
-  const int n = md.n, m = md.m, nj = md.nj, nv = md.nv, nc = md.nc;
-  const int ndyn = 7 + nj + nv, ndir = ndyn + m;
+  const int n = md.n, m = md.m, nj = NJ, nc = NC;
   const bool term = (t == N);
   const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
   const float* Ut = io.U + (size_t(e) * N + t) * m;
@@ -63,49 +81,74 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
   const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
   const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
   const float* W = io.W + size_t(e) * io.w_stride;
+  float* sx = sm.sx;
+  float* su = sm.su;
+  float* svn = sm.svn;
+  float* sgrad = sm.sgrad;
+  float* satv = sm.satv;
+  float* sG = sm.sG;
   for (int i = tid; i < n; i += NT) {
     sx[i] = Xt[i];
     svn[i] = term ? 0.f : Vt[n + i];
     satv[i] = 0.f;
   }
   for (int i = tid; i < m; i += NT) { su[i] = term ? 0.f : Ut[i]; satv[n + i] = 0.f; }
+  if (!term) {
+    for (int i = tid; i < NV * NV; i += NT) sm.k.M[i] = 0.f;
+    for (int i = tid; i < NV * NF; i += NT) sm.k.J[i] = 0.f;
+  }
   __syncthreads();
 
-  // ---- dynamics: primal + one Jacobian column per thread
   if (!term) {
+    // ---- P1: primal tree pass
+    if (tid == 0) {
+      WbStackPlain<float> stk{sm.prim[0]};
+      WbStoreSink<float> sink{sm.k.M, NV, sm.k.D, sm.k.J, NF, sm.k.feet};
+      WbInPlain<float> in{sx, sx + NQ};
+      wb_dfs<float>(md, in, stk, sink);
+    }
+    __syncthreads();
+    // ---- P2: contact solve, next state, constraint residual
+    wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, [] { __syncthreads(); });
+    {
+      float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
+      const float* Xn = Xt + n;
+      for (int i = tid; i < n; i += NT) c[i] = sm.k.xn[i] - Xn[i];
+    }
+    // ---- P3 + P4: one column of [A | B] per thread
     float* A = o.A + (size_t(e) * N + t) * n * n;
     float* B = o.B + (size_t(e) * N + t) * n * m;
-    if (tid < ndir) {
-      Dual x[NX], u[NU], xn[NX];
-      for (int i = 0; i < n; ++i) x[i] = Dual(sx[i], i == tid ? 1.f : 0.f);
-      for (int i = 0; i < m; ++i) u[i] = Dual(su[i], ndyn + i == tid ? 1.f : 0.f);
-      wb_dynamics<Dual, NB, NV, NC>(md, x, u, par, xn);
+    if (tid < NDS + m) {
+      float t1[NV], t2[NV], ee[NV], hh[NF], dfeet[NF];
+      const int is_u = tid >= NDS;
+      if (!is_u) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { t1[i] = 0.f; t2[i] = 0.f; ee[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < NF; ++i) { hh[i] = 0.f; dfeet[i] = 0.f; }
+        WbStackSplit stk{sm.prim[tid >> 5], sm.tan + tid, NDS};
+        WbTangentSink sink{t1, t2, ee, hh, dfeet, sm.k.w, sm.k.z, sm.k.a, sm.k.y, sm.k.grf, sm.k.wvz};
+        WbInSeed seed{sx, NQ, tid};
+        wb_dfs<Dual>(md, seed, stk, sink);
+      }
       float atv = 0.f;
-      if (tid < ndyn) {
-        for (int i = 0; i < n; ++i) { A[i * n + tid] = xn[i].d; atv = fmaf(xn[i].d, svn[i], atv); }
-        satv[tid] = atv;
-      } else {
-        const int ju = tid - ndyn;
-        for (int i = 0; i < n; ++i) { B[i * m + ju] = xn[i].d; atv = fmaf(xn[i].d, svn[i], atv); }
-        satv[n + ju] = atv;
-      }
-      if (tid == 0) {
-        float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
-        const float* Xn = Xt + n;
-        for (int i = 0; i < n; ++i) c[i] = xn[i].v - Xn[i];
-      }
+      float* dst = is_u ? B + (tid - NDS) : A + tid;
+      const int ld = is_u ? m : n;
+      wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet,
+                            [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); });
+      satv[is_u ? n + tid - NDS : tid] = atv;
     }
     // the foot / GRF tail of the state does not enter the dynamics
-    const int ntail = n - ndyn;
+    const int ntail = n - NDS;
     for (int idx = tid; idx < n * ntail; idx += NT) {
-      const int i = idx / ntail, j = ndyn + idx - i * ntail;
+      const int i = idx / ntail, j = NDS + idx - i * ntail;
       A[i * n + j] = 0.f;
     }
   }
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
 
-  // ---- cost value + gradient (forward mode, one direction per thread per pass)
+  // ---- P5: cost value + gradient (forward mode, one direction per thread per pass)
   for (int d = tid; d < n + m; d += NT) {
     if (term && d >= n) break;
     Dual x[NX], u[NU];
@@ -243,19 +286,28 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   }
 }
 
-template <int NB, int NV, int NC, int NT>
+template <int NV, int NC, int MAXD, int NT>
 inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
-  const int ndir = 7 + h.nj + h.nv + h.m;
-  if (ndir > NT) return MPXB_EUNSUPPORTED;
-  wb_linearize_kernel<NB, NV, NC, NT><<<io.E * (io.N + 1), NT, 0, st>>>(dev, io, lo);
+  using S = WbLinSmem<NV, NC, MAXD, NT>;
+  if (h.nv != NV || h.nc != NC || h.maxdepth > MAXD || 2 * NV + 1 + h.m > NT) return MPXB_EUNSUPPORTED;
+  auto kern = wb_linearize_kernel<NV, NC, MAXD, NT>;
+  static bool configured[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 64 && !configured[d]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
+    configured[d] = true;
+  }
+  kern<<<io.E * (io.N + 1), NT, sizeof(S), st>>>(dev, io, lo);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
-// tree-size classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u]
+// tree classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u]
 inline int wb_launch_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
-  if (h.nbody <= 14 && h.nv <= 18 && h.nc <= 4) return wb_launch_linearize_t<14, 18, 4, 64>(h, dev, io, lo, st);
-  if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) return wb_launch_linearize_t<21, 25, 4, 96>(h, dev, io, lo, st);
-  return wb_launch_linearize_t<32, 28, 8, 128>(h, dev, io, lo, st);
+  if (h.nv == 18 && h.nc == 4) return wb_launch_linearize_t<18, 4, 4, 64>(h, dev, io, lo, st);
+  if (h.nv == 25 && h.nc == 4) return wb_launch_linearize_t<25, 4, 6, 96>(h, dev, io, lo, st);
+  if (h.nv == 28 && h.nc == 8) return wb_launch_linearize_t<28, 8, 10, 128>(h, dev, io, lo, st);
+  return MPXB_EUNSUPPORTED;
 }
 
 inline int wb_launch_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {

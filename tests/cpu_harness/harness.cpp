@@ -37,6 +37,46 @@ void cost_t(const WbModel& md, const float* W, const float* ref, const float* x,
     grad[d] = wb_cost<Dual, NJ, NC>(md, W, ref, xd.data(), ud.data(), terminal != 0).d;
   }
 }
+// x+ and [A | B] through the v2 path of the linearise kernel: primal path-stack pass, cooperative contact solve
+// (run by one worker here), one forward-mode path-stack pass per state direction folded by WbTangentSink, and the
+// analytic contact-solve derivative wb_s3_tangent.
+template <int NV, int NC>
+void hybrid_t(const WbModel& md, const float* x, const float* u, const float* contact, float* xn, float* A, float* B) {
+  constexpr int NF = 3 * NC;
+  const int n = md.n, m = md.m, nj = md.nj, nv = md.nv, nq = 7 + nj, nf = 3 * md.nc;
+  static WbKnot<NV, NC> k;
+  static float stack[WB_MAXB * WB_SLOT];
+  static Dual dstack[WB_MAXB * WB_SLOT];
+  for (int i = 0; i < NV * NV; ++i) k.M[i] = 0.f;
+  for (int i = 0; i < NV * NF; ++i) k.J[i] = 0.f;
+  WbStackPlain<float> stk{stack};
+  WbStoreSink<float> sink{k.M, NV, k.D, k.J, NF, k.feet};
+  WbInPlain<float> in{x, x + nq};
+  wb_dfs<float>(md, in, stk, sink);
+  wb_s3_primal<NV, NC>(md, k, x, u, contact, 0, 1, [] {});
+  for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
+  std::vector<float> col(n);
+  for (int d = 0; d < nq + nv + m; ++d) {
+    float t1[NV] = {0}, t2[NV] = {0}, e[NV] = {0}, h[NF] = {0}, dfeet[NF] = {0};
+    const int is_u = d >= nq + nv;
+    if (!is_u) {
+      WbStackPlain<Dual> ds{dstack};
+      WbTangentSink ts{t1, t2, e, h, dfeet, k.w, k.z, k.a, k.y, k.grf, k.wvz};
+      WbInSeed seed{x, nq, d};
+      wb_dfs<Dual>(md, seed, ds, ts);
+    }
+    float* cp = col.data();
+    wb_s3_tangent<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
+                          [cp](int i, float v) { cp[i] = v; });
+    for (int i = 0; i < n; ++i) {
+      if (!is_u) A[i * n + d] = col[i];
+      else B[i * m + d - nq - nv] = col[i];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = nq + nv; j < n; ++j) A[i * n + j] = 0.f;
+}
+
 }  // namespace
 
 extern "C" {
@@ -77,6 +117,35 @@ int h_wb_terms(const mpxb_model_desc* d, const float* qpos, const float* qvel, f
   wb_mass_matrix<float, NB, NV>(md, cinert, cdof, crb, M, md.nv);
   wb_bias<float, float, float, NB, NV>(md, cinert, cdof, qvel, cvel, cacc, cfrc, bias);
   wb_contact_jacobian<float, NV, NC>(md, cdof, com, feet, J, 3 * md.nc);
+  return 0;
+}
+
+// the same terms through the single-pass path-stack evaluation (wb_dfs) that the v2 linearise kernel uses
+int h_wb_terms_dfs(const mpxb_model_desc* d, const float* qpos, const float* qvel, float* M, float* bias, float* J,
+                   float* feet) {
+  WbModel md;
+  int rc = wb_build_model(*d, &md);
+  if (rc) return rc;
+  static float stack[WB_MAXB * WB_SLOT];
+  const int nv = md.nv, nf = 3 * md.nc;
+  for (int i = 0; i < nv * nv; ++i) M[i] = 0.f;
+  for (int i = 0; i < nv * nf; ++i) J[i] = 0.f;
+  WbStackPlain<float> stk{stack};
+  WbStoreSink<float> sink{M, nv, bias, J, nf, feet};
+  WbInPlain<float> in{qpos, qvel};
+  wb_dfs<float>(md, in, stk, sink);
+  return 0;
+}
+
+int h_wb_dynamics_hybrid(const mpxb_model_desc* d, const float* x, const float* u, const float* contact, float* xn,
+                         float* A, float* B) {
+  WbModel md;
+  int rc = wb_build_model(*d, &md);
+  if (rc) return rc;
+  if (md.nv == 18 && md.nc == 4) hybrid_t<18, 4>(md, x, u, contact, xn, A, B);
+  else if (md.nv == 25 && md.nc == 4) hybrid_t<25, 4>(md, x, u, contact, xn, A, B);
+  else if (md.nv == 28 && md.nc == 8) hybrid_t<28, 8>(md, x, u, contact, xn, A, B);
+  else return -2;
   return 0;
 }
 

@@ -66,14 +66,17 @@ def _state(cfg, inp, rng):
     return x, u
 
 
-def test_mjx_terms(H, robot):
+@pytest.mark.parametrize("fn", ["h_wb_terms", "h_wb_terms_dfs"])
+def test_mjx_terms(H, robot, fn):
+    """qM, qfrc_bias, foot Jacobians and foot positions: the COM-centred arrays form (trial kernel) and the
+    single-pass path-stack form about the base position (linearise kernel) against the restated MJX."""
     cfg, pr, inp, desc = robot
     rng = np.random.default_rng(0)
     x, _ = _state(cfg, inp, rng)
     nq, nv, nc = 7 + cfg.n_joints, 6 + cfg.n_joints, cfg.n_contact
     qpos, qvel = x[:nq], x[nq:nq + nv]
     M, bias, J, feet = (np.zeros(s, np.float32) for s in ((nv, nv), (nv,), (nv, 3 * nc), (3 * nc,)))
-    assert H.h_wb_terms(C.byref(desc), _p(_f(qpos)), _p(_f(qvel)), _p(M), _p(bias), _p(J), _p(feet)) == 0
+    assert getattr(H, fn)(C.byref(desc), _p(_f(qpos)), _p(_f(qvel)), _p(M), _p(bias), _p(J), _p(feet)) == 0
     d = mjx_smooth.fwd_position(pr.m, torch.as_tensor(qpos))
     d = mjx_smooth.fwd_velocity(pr.m, d, torch.as_tensor(qvel))
     per_foot = [desc.contact_body[i] for i in range(nc)]
@@ -87,8 +90,11 @@ def test_mjx_terms(H, robot):
     assert abs(M[0, 0] - pr.robot_mass) / pr.robot_mass < 1e-5
 
 
+@pytest.mark.parametrize("fn", ["h_wb_dynamics", "h_wb_dynamics_hybrid"])
 @pytest.mark.parametrize("contact_pattern", ["all", "trot"])
-def test_dynamics_and_jacobians(H, robot, contact_pattern):
+def test_dynamics_and_jacobians(H, robot, contact_pattern, fn):
+    """x+ = f(x,u), A = df/dx, B = df/du: plain forward mode through the whole dynamics (h_wb_dynamics) and the
+    kernel's path-stack + analytic contact-solve derivative (h_wb_dynamics_hybrid) against jacrev of the oracle."""
     cfg, pr, inp, desc = robot
     rng = np.random.default_rng(1)
     x, u = _state(cfg, inp, rng)
@@ -96,7 +102,7 @@ def test_dynamics_and_jacobians(H, robot, contact_pattern):
     contact = np.ones(nc) if contact_pattern == "all" else (np.arange(nc) % 2).astype(np.float64)
     par = np.tile(contact, (cfg.N + 1, 1))
     xn, A, B = np.zeros(n, np.float32), np.zeros((n, n), np.float32), np.zeros((n, m), np.float32)
-    assert H.h_wb_dynamics(C.byref(desc), _p(_f(x)), _p(_f(u)), _p(_f(contact)), _p(xn), _p(A), _p(B)) == 0
+    assert getattr(H, fn)(C.byref(desc), _p(_f(x)), _p(_f(u)), _p(_f(contact)), _p(xn), _p(A), _p(B)) == 0
     xt, ut, pt = torch.as_tensor(x), torch.as_tensor(u), torch.as_tensor(par)
     f = lambda x_, u_: pr.dynamics(x_, u_, 0, pt)
     Ao, Bo = jacrev(f, 0)(xt, ut), jacrev(f, 1)(xt, ut)
