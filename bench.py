@@ -280,6 +280,7 @@ def run_native(args):
     lib.mpxb_profile_attach(solver.handle, None)
     lib.mpxb_profile_destroy(prof)
     nonfinite_envs = int((~torch.isfinite(X).flatten(1).all(1)).sum().item())
+    alpha_hist = torch.bincount(solver.alpha_index.to(torch.int64), minlength=11).tolist()
     tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -368,7 +369,8 @@ def run_native(args):
                            "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
                            "parallelism": f"env-sharded x{world}, no collective on the solve path"},
                 "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "clocks": clocks, "nonfinite_envs": nonfinite_envs}
+                "clocks": clocks, "nonfinite_envs": nonfinite_envs,
+                "alpha_index_hist_last_step": alpha_hist}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

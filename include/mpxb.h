@@ -151,6 +151,33 @@ size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m);
  * Replaces the host-side MuJoCo mj_kinematics + geom_xpos read of mpc_wrapper.py:313-318 / 373-376 (whole-body kinds). */
 int mpxb_wb_foot_positions(const mpxb_model* model, void* stream, int E, const float* qpos, float* feet);
 
+/* Gait timer + swing / foothold reference generator, batched over E and stream-ordered: the step immediately before
+ * the solve in every wrapper tick.  Replaces timer_run (mpx/utils/mpc_utils.py:7-14), reference_generator (38-144,
+ * whole-body kinds) and reference_generator_srbd (146-270, MPXB_KIND_SRBD) as the wrappers call them
+ * (mpc_wrapper.py:132-147, 329-343; mpc_wrapper_srbd.py:103-121).
+ *   x [E,n] measured state; foot: rows of `foot_stride` floats whose first 3*n_contact entries are the measured foot
+ *   positions (may point into x); input [E,7] command; contact [E,n_contact] measured contact flags or NULL (= 0, as the
+ *   batched whole-body wrapper passes, mpc_wrapper.py:134);
+ *   timer_in [E,n_contact] gait phase; timer_out (may be NULL or alias timer_in) receives the phase advanced by
+ *   gait->mpc_dt * step_freq (timer_run); the generator itself starts from timer_in (advance_timer_first = 0, batched
+ *   whole-body wrapper) or from the advanced phase (advance_timer_first = 1, single-instance and SRBD wrappers);
+ *   liftoff [E,3*n_contact] updated in place;
+ *   reference [E,N+1,nref], parameter [E,N+1,npar] outputs; foot_ref_dot [E,N+1,3*n_contact] output or NULL. */
+typedef struct mpxb_gait {
+  int32_t use_terrain_estimation; /* config.use_terrain_estimation (needs n_contact == 4) */
+  int32_t advance_timer_first;
+  float mpc_dt;                   /* 1 / config.mpc_frequency */
+  float duty_factor, step_freq, step_height;
+  float mass;                     /* robot mass used for the GRF reference */
+  float clearence_speed;
+  float foot0[3 * MPXB_MAX_CONTACT]; /* config.p_legs0 */
+  float q0[MPXB_MAX_DOF];            /* config.q0 (whole-body kinds) */
+} mpxb_gait;
+int mpxb_reference_generator(const mpxb_model* model, void* stream, int E, const mpxb_gait* gait, const float* x,
+                             const float* foot, int foot_stride, const float* input, const float* contact,
+                             const float* timer_in, float* timer_out, float* liftoff, float* reference,
+                             float* parameter, float* foot_ref_dot);
+
 /* Per-kernel timing for benchmarks (bench.py roofline): once attached, every mpxb_mpc_step on `model` records CUDA
  * events on its stream at the boundaries of the four kernels of the LAST SQP iteration of the call
  * (linearise | LQ solve | line-search trials | select/update).  Up to `max_calls` calls are kept (later calls are

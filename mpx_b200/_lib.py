@@ -33,6 +33,12 @@ class ModelDesc(C.Structure):
     ]
 
 
+class Gait(C.Structure):
+    _fields_ = [("use_terrain_estimation", C.c_int32), ("advance_timer_first", C.c_int32), ("mpc_dt", C.c_float),
+                ("duty_factor", C.c_float), ("step_freq", C.c_float), ("step_height", C.c_float), ("mass", C.c_float),
+                ("clearence_speed", C.c_float), ("foot0", C.c_float * (3 * MAX_CONTACT)), ("q0", C.c_float * MAX_DOF)]
+
+
 _lib = None
 
 
@@ -67,6 +73,8 @@ def lib():
     L.mpxb_tvlqr_scan_bytes.restype = sz
     L.mpxb_wb_foot_positions.argtypes = [vp, vp, i32, f32p, f32p]
     L.mpxb_wb_foot_positions.restype = i32
+    L.mpxb_reference_generator.argtypes = [vp, vp, i32, C.POINTER(Gait), f32p, f32p, i32] + [f32p] * 8
+    L.mpxb_reference_generator.restype = i32
     L.mpxb_profile_create.argtypes = [i32, C.POINTER(vp)]
     L.mpxb_profile_create.restype = i32
     L.mpxb_profile_destroy.argtypes = [vp]
@@ -170,3 +178,18 @@ def make_desc(config, robot_model=None):
         if rm.geom_bodyid[g] != b:
             raise ValueError("contact geom is not attached to the body the dynamics pair it with")
     return d
+
+
+def make_gait(config, mass, duty_factor, step_freq, step_height, clearence_speed, use_terrain, advance_timer_first):
+    """config + the wrapper's (mutable) gait attributes -> Gait for mpxb_reference_generator."""
+    g = Gait()
+    g.use_terrain_estimation = int(bool(use_terrain))
+    g.advance_timer_first = int(bool(advance_timer_first))
+    g.mpc_dt = 1.0 / float(config.mpc_frequency)
+    g.duty_factor, g.step_freq, g.step_height = float(duty_factor), float(step_freq), float(step_height)
+    g.mass, g.clearence_speed = float(mass), float(clearence_speed)
+    _fill(g.foot0, np.asarray(config.p_legs0, dtype=np.float64).reshape(-1))
+    q0 = getattr(config, "q0", None)
+    if q0 is not None and len(np.asarray(q0).reshape(-1)) <= MAX_DOF:
+        _fill(g.q0, np.asarray(q0, dtype=np.float64).reshape(-1))
+    return g

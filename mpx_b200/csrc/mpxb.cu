@@ -17,6 +17,7 @@
 #include "srbd_kernels.cuh"
 #include "wb_kernels.cuh"
 #include "lq_scan.cuh"
+#include "refgen.cuh"
 
 using namespace mpxb;
 
@@ -250,6 +251,26 @@ int mpxb_wb_foot_positions(const mpxb_model* mdl, void* stream, int E, const flo
   else if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) wb_feet_kernel<21, 25, 4><<<nb, nt, 0, st>>>(mdl->wb_dev, E, qpos, feet);
   else wb_feet_kernel<32, 28, 8><<<nb, nt, 0, st>>>(mdl->wb_dev, E, qpos, feet);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+int mpxb_reference_generator(const mpxb_model* mdl, void* stream, int E, const mpxb_gait* g, const float* x,
+                             const float* foot, int foot_stride, const float* input, const float* contact,
+                             const float* timer_in, float* timer_out, float* liftoff, float* reference,
+                             float* parameter, float* foot_ref_dot) {
+  if (!mdl || !g || !x || !foot || !input || !timer_in || !liftoff || !reference || !parameter || E <= 0) return MPXB_EINVAL;
+  const mpxb_model_desc& d = mdl->desc;
+  if (g->use_terrain_estimation && d.n_contact != 4) return MPXB_EINVAL;
+  if (foot_stride < 3 * d.n_contact || d.n_contact > MPXB_MAX_CONTACT) return MPXB_EINVAL;
+  RefGenArgs a;
+  a.E = E; a.N = d.N; a.nc = d.n_contact; a.srbd = d.kind == MPXB_KIND_SRBD; a.nj = a.srbd ? 0 : d.n_joints; a.n = d.n;
+  a.use_terrain = g->use_terrain_estimation; a.advance_first = g->advance_timer_first;
+  a.dt = d.dt; a.mpc_dt = g->mpc_dt; a.duty_factor = g->duty_factor; a.step_freq = g->step_freq;
+  a.step_height = g->step_height; a.mass = g->mass; a.clearence_speed = g->clearence_speed;
+  memcpy(a.foot0, g->foot0, sizeof(a.foot0));
+  memcpy(a.q0, g->q0, sizeof(a.q0));
+  a.x = x; a.foot = foot; a.foot_stride = foot_stride; a.input = input; a.contact = contact; a.timer_in = timer_in;
+  a.timer_out = timer_out; a.liftoff = liftoff; a.reference = reference; a.parameter = parameter; a.foot_ref_dot = foot_ref_dot;
+  return launch_refgen(a, static_cast<cudaStream_t>(stream));
 }
 
 int mpxb_profile_create(int max_calls, mpxb_profile** out) {

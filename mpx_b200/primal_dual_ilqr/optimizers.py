@@ -127,6 +127,25 @@ class MpcSolver:
                   "slope": (E,)}
         return flat.view(shapes[name])
 
+    def reference_generator(self, gait, x, foot, foot_stride, input, contact, timer_in, timer_out, liftoff,
+                            want_foot_ref_dot=False):
+        """mpxb_reference_generator: gait timer + reference generator on the device (mpc_utils.py:7-14, 38-270).
+
+        ``gait`` is a ``_lib.Gait``; ``foot`` may be a strided view into ``x`` (pass its row stride).  ``liftoff`` is
+        updated in place, ``timer_out`` receives the advanced gait phase.  Returns (reference, parameter[, foot_ref_dot])."""
+        E, N = self.n_env, self.N
+        nc = self.desc.n_contact
+        mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        reference, parameter = mk(E, N + 1, self.nref), mk(E, N + 1, self.npar)
+        frd = mk(E, N + 1, 3 * nc) if want_foot_ref_dot else None
+        p = lambda t: t.data_ptr() if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.mpxb_reference_generator(self.handle, stream, E, C.byref(gait), p(x), p(foot), int(foot_stride),
+                                               p(input), p(contact), p(timer_in), p(timer_out), p(liftoff),
+                                               p(reference), p(parameter), p(frd))
+        _lib.check(rc, "mpxb_reference_generator")
+        return (reference, parameter, frd) if want_foot_ref_dot else (reference, parameter)
+
     def shift_extract(self, X, U, V, x0, u_ref, X0, U0, V0, shift, want_cmd=True):
         """update_and_extract_helper (mpc_wrapper.py:79-98): in-place update of the warm start (X0,U0,V0)."""
         E, nj = self.n_env, self.desc.n_joints

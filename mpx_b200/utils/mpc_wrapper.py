@@ -76,6 +76,14 @@ class _Base:
         self.u_ref = self._T(config.u_ref)
         self.W = self._T(config.W)
 
+    def _gait(self, duty_factor, step_freq, step_height, clearence_speed, advance_first):
+        key = (float(duty_factor), float(step_freq), float(step_height), float(clearence_speed), bool(advance_first))
+        if getattr(self, "_gait_key", None) != key:
+            self._gait_key = key
+            self._gait_struct = _lib.make_gait(self.config, self.robot_mass, key[0], key[1], key[2], key[3],
+                                               self.config.use_terrain_estimation, advance_first)
+        return self._gait_struct
+
     def _as(self, t):
         if not torch.is_tensor(t):
             t = torch.as_tensor(np.asarray(t), dtype=torch.float32)
@@ -118,13 +126,15 @@ class BatchedMPCControllerWrapper(_Base):
         cfg = self.config
         nj, nc = cfg.n_joints, cfg.n_contact
         x0, input = self._as(x0), self._as(input)
-        _, contact_time = mpc_utils.timer_run(data.duty_factor, data.step_freq, data.contact_time, 1 / self.mpc_frequency)
-        contact = torch.zeros(self.n_env, nc, device=self.device)
-        reference, parameter, liftoff = self.reference_generator(
-            duty_factor=data.duty_factor, step_freq=data.step_freq, step_height=data.step_height,
-            t_timer=data.contact_time, x=x0, foot=x0[:, 13 + 2 * nj:13 + 2 * nj + 3 * nc], input=input,
-            liftoff=data.liftoff, contact=contact)
-        reference, parameter = reference.contiguous(), parameter.contiguous()
+        # gait timer + reference generator: one kernel (mpc_wrapper.py:132-147; the batched wrapper feeds the generator
+        # the phase BEFORE this tick's timer advance, contact = 0 and clearence_speed = 0.2)
+        x0 = x0.contiguous()
+        gait = self._gait(data.duty_factor, data.step_freq, data.step_height, 0.2, False)
+        contact_time = torch.empty_like(data.contact_time)
+        liftoff = data.liftoff.clone()
+        reference, parameter = self._solver.reference_generator(
+            gait, x0, x0[:, 13 + 2 * nj:], x0.shape[1], input.contiguous(), None, data.contact_time.contiguous(),
+            contact_time, liftoff)
         self.reference, self.parameter = reference, parameter
         X, U, V = self._solver.solve(reference, parameter, data.W, x0, data.X0, data.U0, data.V0)
         X0, U0, V0 = torch.empty_like(data.X0), torch.empty_like(data.U0), torch.empty_like(data.V0)
@@ -199,11 +209,12 @@ class MPCControllerWrapper(_Base):
         input = np.array(input, dtype=np.float64)
         input[6] = self.robot_height
         contact_t = self._as(np.asarray(contact, dtype=np.float32))[None]
-        _, self.contact_time = self._timer_run(self.duty_factor, self.step_freq, self.contact_time, 1 / self.mpc_frequency)
-        reference, parameter, self.liftoff = self._ref_gen(
-            duty_factor=self.duty_factor, step_freq=self.step_freq, step_height=self.step_height,
-            t_timer=self.contact_time.clone(), x=x0, foot=foot_op, input=self._as(input)[None], liftoff=self.liftoff,
-            contact=contact_t, clearence_speed=self.clearence_speed)
+        # mpc_wrapper.py:329-343: the timer advances first and the generator starts from the advanced phase
+        gait = self._gait(self.duty_factor, self.step_freq, self.step_height, self.clearence_speed, True)
+        reference, parameter = self._solver.reference_generator(
+            gait, x0, foot_op, foot_op.shape[1], self._as(input)[None].contiguous(), contact_t.contiguous(),
+            self.contact_time, self.contact_time, self.liftoff)
+        self.reference, self.parameter = reference, parameter
         X, U, V = self._solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
         tau, q, dq = self._solver.shift_extract(X, U, V, x0, self.u_ref, self.X0, self.U0, self.V0, self.shift)
         self.X, self.U, self.V = X, U, V

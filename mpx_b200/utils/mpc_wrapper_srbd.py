@@ -13,6 +13,7 @@ import mpx_b200.utils.mpc_utils as mpc_utils
 import mpx_b200.utils.models as mpc_dyn_model
 import mpx_b200.utils.objectives as mpc_objectives
 import mpx_b200.primal_dual_ilqr.optimizers as optimizers
+from mpx_b200 import _lib
 
 
 class BatchedMPCControllerWrapper:
@@ -45,6 +46,8 @@ class BatchedMPCControllerWrapper:
                                 duty_factor=config.duty_factor, step_freq=config.step_freq,
                                 step_height=config.step_height, foot0=config.p_legs0)
         self._timer_run = mpc_utils.timer_run
+        self._gait = _lib.make_gait(config, config.mass, config.duty_factor, config.step_freq, config.step_height,
+                                    config.clearence_speed, config.use_terrain_estimator, True)
         self.W = T(config.W)
         self.u_ref = T(config.u_ref)
         self.reset(verbose=False)
@@ -55,11 +58,13 @@ class BatchedMPCControllerWrapper:
     def run(self, x0, input, foot_op, contact):
         """One MPC update (mpc_wrapper_srbd.py:91-141). All arguments [n_env, ...] CUDA tensors."""
         x0, input, foot_op, contact = (self._as(t) for t in (x0, input, foot_op, contact))
-        self.contact, self.contact_time = self._timer_run(self.config.duty_factor, self.config.step_freq,
-                                                          self.contact_time, 1 / self.mpc_frequency)
-        reference, parameter, self.liftoff, foot_ref_dot = self._ref_gen(
-            t_timer=self.contact_time.clone(), x=x0, foot=foot_op, input=input, contact=contact, liftoff=self.liftoff)
-        reference, parameter = reference.contiguous(), parameter.contiguous()
+        cfg = self.config
+        x0, input, foot_op, contact = (t.contiguous() for t in (x0, input, foot_op, contact))
+        # mpc_wrapper_srbd.py:103-121: timer advance, then the generator from the advanced phase -- one kernel
+        reference, parameter, foot_ref_dot = self._solver.reference_generator(
+            self._gait, x0, foot_op, foot_op.shape[1], input, contact, self.contact_time, self.contact_time, self.liftoff,
+            want_foot_ref_dot=True)
+        self.contact = (self.contact_time < cfg.duty_factor).to(torch.float32)
         self.reference, self.parameter = reference, parameter
         self.foot_ref = parameter[:, 0, 4:]
         self.foot_ref_dot = foot_ref_dot[:, 0, :]
