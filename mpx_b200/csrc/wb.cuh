@@ -18,6 +18,7 @@
 namespace mpxb {
 
 constexpr int WB_MAXB = 32, WB_MAXV = 32, WB_MAXC = 8;
+constexpr int WB_MAXLEAF = 12, WB_MAXPATH = 12, WB_MAXDIR = 4 + 2 * WB_MAXV, WB_MAXITEMS = 1024;
 constexpr int WB_JNT_FREE = 0, WB_JNT_HINGE = 3;
 
 struct WbModel {
@@ -34,6 +35,17 @@ struct WbModel {
   uint32_t contact_dofmask[WB_MAXC];  // dofs whose body is the contact body or one of its ancestors
   int depth[WB_MAXB];                 // base = 0 (bodies are numbered depth-first, parents before children)
   int maxdepth;
+  // tables of the analytic linearisation (wb_tree.cuh).  Bodies are numbered depth-first, so the subtree of body b
+  // is the index range [b, b + sub_size[b]).  Directions: 0..3 raw base-quaternion components, 4..4+nj-1 hinge
+  // positions (dof D+2), then the nv velocities; items enumerate (direction, body in the direction's subtree).
+  int tree_ok;                        // 0: tables exceed the static bounds, use the forward-mode path
+  int sub_size[WB_MAXB];
+  uint32_t dof_anc[WB_MAXV];          // ancestor dofs of dof i, including i
+  int nleaf, leaf_len[WB_MAXLEAF], leaf_path[WB_MAXLEAF][WB_MAXPATH];
+  int ndir, nitems;
+  uint16_t dir_off[WB_MAXDIR];
+  uint8_t dir_b0[WB_MAXDIR], dir_nb[WB_MAXDIR];
+  uint8_t item_dir[WB_MAXITEMS];
 };
 
 // mpxb_model_desc (host, include/mpxb.h) -> WbModel: derived dof tables and contact ancestor masks
@@ -98,6 +110,45 @@ inline int wb_build_model(const mpxb_model_desc& d, WbModel* o) {
       for (int k = 0; k < w.nv; ++k)
         if (w.dof_body[k] == b) mask |= (1u << k);
     w.contact_dofmask[c] = mask;
+  }
+  // ---- analytic-linearisation tables
+  w.tree_ok = 1;
+  for (int b = w.nbody - 1; b >= 1; --b) {
+    w.sub_size[b] += 1;
+    if (b > 1) w.sub_size[w.parent[b]] += w.sub_size[b];
+  }
+  for (int b = 2; b < w.nbody; ++b) {  // depth-first numbering <=> every subtree is a contiguous index range
+    const int p = w.parent[b];
+    if (!(b > p && b < p + w.sub_size[p])) w.tree_ok = 0;
+  }
+  for (int i = 0; i < w.nv; ++i) {
+    uint32_t mk = 0;
+    for (int j = i; j >= 0; j = w.dof_parent[j]) mk |= (1u << j);
+    w.dof_anc[i] = mk;
+  }
+  w.nleaf = 0;
+  for (int b = 1; b < w.nbody; ++b) {
+    bool leaf = true;
+    for (int c = b + 1; c < w.nbody; ++c) leaf = leaf && (w.parent[c] != b);
+    if (!leaf) continue;
+    if (w.nleaf >= WB_MAXLEAF || w.depth[b] + 1 > WB_MAXPATH) { w.tree_ok = 0; break; }
+    const int len = w.depth[b] + 1;
+    w.leaf_len[w.nleaf] = len;
+    int a = b;
+    for (int l = len - 1; l >= 0; --l) { w.leaf_path[w.nleaf][l] = a; a = w.parent[a]; }
+    ++w.nleaf;
+  }
+  w.ndir = 4 + w.nj + w.nv;
+  w.nitems = 0;
+  for (int D = 0; D < w.ndir && w.tree_ok; ++D) {
+    int b0 = 1;
+    if (D >= 4 && D < 4 + w.nj) b0 = w.dof_body[D + 2];
+    else if (D >= 4 + w.nj) b0 = w.dof_body[D - 4 - w.nj];
+    w.dir_b0[D] = uint8_t(b0);
+    w.dir_nb[D] = uint8_t(w.sub_size[b0]);
+    w.dir_off[D] = uint16_t(w.nitems);
+    if (w.nitems + w.sub_size[b0] > WB_MAXITEMS) { w.tree_ok = 0; break; }
+    for (int k = 0; k < w.sub_size[b0]; ++k) w.item_dir[w.nitems++] = uint8_t(D);
   }
   return MPXB_OK;
 }

@@ -10,6 +10,8 @@
 #include "../../include/mpxb.h"
 #include "srbd_kernels.cuh"
 #include "wb.cuh"
+#include "wb_tree.cuh"
+#include <stdlib.h>
 
 namespace mpxb {
 
@@ -38,6 +40,220 @@ __device__ __forceinline__ WbResMap wb_resmap_x(const WbModel& md, int j, const 
   return r;
 }
 
+// Shared-memory scratch of wb_knot_cost_blocks
+template <int NV, int NC> struct WbCostSmem {
+  static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NW = 12 + 3 * NJ + 2 * NF;
+  float r[NW], y[NW], part[NW], pen[NX + NU], dpen[NX + NU], rc[NX];
+  int ra[NX];
+};
+
+// d penalty / dc with the reference's clip / where derivative conventions (forward mode on the scalar)
+__device__ __forceinline__ Dual wb_pen(float c, float sgn, float alpha, float sigma) {
+  const Dual p = penalty(Dual(c, sgn), alpha, sigma);
+  return p;
+}
+
+// P5 of the linearise kernels: cost value + gradient, q, r and the Gauss-Newton blocks Q, R, M of one knot.
+// sx / su / satv / sgrad / sG live in shared memory; satv holds [A | B]^T V_{t+1}.
+//
+// The reference takes jax.grad of the cost (optimizers.py:111-120,165-169 through trajax linearize/quadratize); the
+// cost is 0.5 * sum_blocks r_b' W_bb r_b + penalties (objectives.py:77-125, 204-250, 325-376), every residual is
+// an identity map of one entry of (x, u) except the 3x4 quaternion-error block, so the gradient is assembled in
+// closed form: y = 0.5 (W_bb + W_bb') r_b, grad = (dr/dx)' y + penalty slopes.
+template <int NV, int NC, int NT>
+__device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
+                                                    const float* sx, const float* su, float* sgrad, const float* satv,
+                                                    float* sG, WbCostSmem<NV, NC>& cs) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  const int tid = threadIdx.x;
+  const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
+  const bool term = (t == N);
+  const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+  const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
+  const float* W = io.W + size_t(e) * io.w_stride;
+  const int nw = md.nw;
+  const float* contact = ref + 13 + nj + nf;
+  const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
+  const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
+  const bool quad = (md.kind == MPXB_KIND_QUAD_WB);
+  const bool masked = quad && !md.swing_tracking;  // contact_map (objectives.py:110-113)
+  // block boundaries of the residual vector
+  const int bb[10] = {0, 3, 6, 6 + nj, 9 + nj, 12 + nj, 12 + 2 * nj, ua0, ua0 + nj, ua0 + nj + nf};
+  const int nact = term ? 12 + 2 * nj : nw;  // the terminal cost drops the foot / torque / GRF terms
+
+  // ---- residuals, the quaternion-error Jacobian, the residual map of every state entry
+  for (int a = tid; a < nw; a += NT) {
+    float r = 0.f;
+    if (a < 3) r = sx[a] - ref[a];
+    else if (a < 6) r = 0.f;  // filled below
+    else if (a < 12 + nj) r = sx[a + 1] - ref[a + 1];
+    else if (a < 12 + 2 * nj) r = sx[a + 1];
+    else if (a < ua0) {
+      r = sx[a + 1] - ref[a + 1 - nj];
+      if (masked) r *= contact[(a - 12 - 2 * nj) / 3];
+    } else if (a < ua0 + nj) r = su[a - ua0];
+    else {
+      const int i = a - ua0 - nj;
+      r = (md.grf_in_u ? su[nj + i] : sx[g0 + i]) - ref[13 + nj + nf + nc + i];
+    }
+    if (a < 3 || a >= 6) cs.r[a] = (a < nact) ? r : 0.f;
+  }
+  if (tid < 4) {
+    Dual q[4], rs[3];
+    for (int i = 0; i < 4; ++i) q[i] = Dual(sx[3 + i], i == tid ? 1.f : 0.f);
+    quat_sub(q, ref + 3, rs);
+    for (int k = 0; k < 3; ++k) {
+      sG[k * 4 + tid] = rs[k].d;
+      if (tid == 0) cs.r[3 + k] = rs[k].v;
+    }
+  }
+  for (int j = tid; j < n; j += NT) {
+    int a = j - 1;
+    float c = 1.f;
+    if (j < 3) a = j;
+    else if (j < 7) a = -1;
+    else if (j >= 13 + 2 * nj && j < g0) { if (masked) c = contact[(j - 13 - 2 * nj) / 3]; }
+    else if (j >= g0) a = j - 1 + nj;
+    cs.ra[j] = a;
+    cs.rc[j] = c;
+  }
+  // ---- penalties (quadruped only): value and slope per owning variable
+  for (int d = tid; d < n + m; d += NT) {
+    float pv = 0.f, pd = 0.f;
+    if (quad && !term) {
+      if (d >= v0 && d < v0 + nj) {  // joint speed +-10
+        const Dual p1 = wb_pen(10.01f - sx[d], -1.f, 1.f, 1.f), p2 = wb_pen(sx[d] + 10.01f, 1.f, 1.f, 1.f);
+        pv = p1.v + p2.v; pd = p1.d + p2.d;
+      } else if (d >= n && d < n + nj) {  // torque +-44
+        const float tq = su[d - n];
+        const Dual p1 = wb_pen(44.01f - tq, -1.f, 1.f, 1.f), p2 = wb_pen(tq + 44.01f, 1.f, 1.f, 1.f);
+        pv = p1.v + p2.v; pd = p1.d + p2.d;
+      } else if (d >= g0 && d < g0 + nf) {  // friction cone (mu 0.5, eps 1e-2), masked by contact
+        const int c = (d - g0) / 3, k = d - g0 - 3 * c;
+        const float gx = sx[g0 + 3 * c], gy = sx[g0 + 3 * c + 1], gz = sx[g0 + 3 * c + 2];
+        const float sq = sqrtf(gy * gy + gx * gx + 1e-2f);
+        const Dual p = wb_pen(0.5f * gz - sq, 1.f, 0.1f, 5.f);
+        const float jf = (k == 0) ? -gx / sq : (k == 1 ? -gy / sq : 0.5f);
+        pd = p.d * jf * contact[c];
+        pv = (k == 2) ? p.v * contact[c] : 0.f;
+      }
+    }
+    cs.pen[d] = pv;
+    cs.dpen[d] = pd;
+  }
+  __syncthreads();
+  // ---- y = 0.5 (W_bb + W_bb') r_b ; cost parts r_a (W_bb r_b)_a
+  for (int a = tid; a < nw; a += NT) {
+    float s1 = 0.f, s2 = 0.f;
+    if (a < nact) {
+      int blk = 0;
+#pragma unroll
+      for (int k = 1; k < 9; ++k) blk += (a >= bb[k]) ? 1 : 0;
+      const int lo = bb[blk], hi = bb[blk + 1];
+      for (int b = lo; b < hi; ++b) {
+        const float rb = cs.r[b];
+        s1 = fmaf(W[a * nw + b], rb, s1);
+        s2 = fmaf(W[b * nw + a], rb, s2);
+      }
+    }
+    cs.y[a] = 0.5f * (s1 + s2);
+    cs.part[a] = cs.r[a] * s1;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int a = tid; a < nw; a += 32) s += cs.part[a];
+    for (int d = tid; d < n + m; d += 32) s += cs.pen[d];
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (tid == 0) o.cost[size_t(e) * (N + 1) + t] = 0.5f * s;
+  }
+  // q_t = grad_x cost + A^T V_{t+1} - V_t ; r_t = grad_u cost + B^T V_{t+1}   (optimizers.py:111-120,165-169)
+  for (int j = tid; j < n; j += NT) {
+    float gj;
+    if (j >= 3 && j < 7) gj = sG[j - 3] * cs.y[3] + sG[4 + j - 3] * cs.y[4] + sG[8 + j - 3] * cs.y[5];
+    else gj = cs.rc[j] * cs.y[cs.ra[j]];
+    gj = fmaf(0.5f, cs.dpen[j], gj);
+    sgrad[j] = gj;
+    o.q[(size_t(e) * (N + 1) + t) * n + j] = gj + satv[j] - Vt[j];
+  }
+  if (!term)
+    for (int i = tid; i < m; i += NT) {
+      const float gi = fmaf(0.5f, cs.dpen[n + i], cs.y[ua0 + i]);
+      sgrad[n + i] = gi;
+      o.r[(size_t(e) * N + t) * m + i] = gi + satv[n + i];
+    }
+
+  // ---- Gauss-Newton blocks Q = Jx^T W Jx (+ penalty curvature), R, M   (objectives.py:127-202, 252-323, 378-450)
+  float* Q = o.Q + (size_t(e) * (N + 1) + t) * n * n;
+  for (int j = tid; j < n; j += NT) {
+    const int aj = cs.ra[j];
+    const float cj = cs.rc[j];
+    const bool jq = aj < 0;
+    float gq[3] = {0.f, 0.f, 0.f};
+    if (jq) { gq[0] = sG[j - 3]; gq[1] = sG[4 + j - 3]; gq[2] = sG[8 + j - 3]; }
+    // W column(s) of j folded with the quaternion map: wj(a) = sum_b W[a][b] (dr_b / dx_j)
+    float curv_speed = 0.f;
+    if (quad && j >= v0 && j < v0 + nj) {
+      const float dq = sx[j];
+      curv_speed = fminf(fmaxf(penalty_dd(10.01f - dq, 0.1f, 5.f), -1e6f), 1e6f) +
+                   fminf(fmaxf(penalty_dd(dq + 10.01f, 0.1f, 5.f), -1e6f), 1e6f);
+    }
+    float hcone = 0.f, jfj = 0.f, jf3[3] = {0.f, 0.f, 0.f};
+    const int cj_foot = (quad && j >= g0) ? (j - g0) / 3 : -1;
+    if (cj_foot >= 0) {
+      // friction cone curvature: eps = 1e-1 here (objectives.py:167), clip +-1e6, masked by contact
+      const float gx = sx[g0 + 3 * cj_foot], gy = sx[g0 + 3 * cj_foot + 1], gz = sx[g0 + 3 * cj_foot + 2];
+      const float sq = sqrtf(gy * gy + gx * gx + 1e-1f);
+      hcone = fminf(fmaxf(penalty_dd(0.5f * gz - sq, 0.1f, 5.f), -1e6f), 1e6f) * contact[cj_foot];
+      jf3[0] = -gx / sq; jf3[1] = -gy / sq; jf3[2] = 0.5f;
+      jfj = jf3[j - g0 - 3 * cj_foot];
+    }
+    for (int i = 0; i < n; ++i) {
+      const int ai = cs.ra[i];
+      float s;
+      if (ai >= 0) {
+        const float ci = cs.rc[i];
+        if (!jq) s = ci * cj * W[ai * nw + aj];
+        else s = ci * (gq[0] * W[ai * nw + 3] + gq[1] * W[ai * nw + 4] + gq[2] * W[ai * nw + 5]);
+      } else {
+        s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float gi = sG[k * 4 + i - 3];
+          if (!jq) s = fmaf(gi * cj, W[(3 + k) * nw + aj], s);
+          else s = fmaf(gi, gq[0] * W[(3 + k) * nw + 3] + gq[1] * W[(3 + k) * nw + 4] + gq[2] * W[(3 + k) * nw + 5], s);
+        }
+      }
+      if (cj_foot >= 0 && i >= g0 && (i - g0) / 3 == cj_foot) s = fmaf(hcone * jf3[i - g0 - 3 * cj_foot], jfj, s);
+      if (i == j) s += curv_speed;
+      Q[i * n + j] = s;
+    }
+  }
+  if (!term) {
+    float* M = o.M + (size_t(e) * N + t) * n * m;
+    for (int idx = tid; idx < n * m; idx += NT) {
+      const int i = idx / m, j = idx - i * m;
+      const int ai = cs.ra[i];
+      float s;
+      if (ai >= 0) s = cs.rc[i] * W[ai * nw + ua0 + j];
+      else s = sG[i - 3] * W[3 * nw + ua0 + j] + sG[4 + i - 3] * W[4 * nw + ua0 + j] + sG[8 + i - 3] * W[5 * nw + ua0 + j];
+      M[idx] = s;
+    }
+    float* R = o.R + (size_t(e) * N + t) * m * m;
+    for (int idx = tid; idx < m * m; idx += NT) {
+      const int i = idx / m, j = idx - i * m;
+      float s = W[(ua0 + i) * nw + ua0 + j];
+      if (quad && i == j && i < nj) {
+        const float tq = su[i];
+        s += fminf(fmaxf(penalty_dd(44.01f - tq, 1.f, 1.f), -1e6f), 1e6f) +
+             fminf(fmaxf(penalty_dd(tq + 44.01f, 1.f, 1.f), -1e6f), 1e6f);
+      }
+      R[idx] = s;
+    }
+  }
+}
+
 // Forward-mode path stack of the linearise kernel: the primal half is identical in every lane and lives once per
 // warp, the tangent half is private to the lane (direction) and lane-interleaved in shared memory.
 struct WbStackSplit {
@@ -52,6 +268,7 @@ template <int NV, int NC, int MAXD, int NT> struct WbLinSmem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
   WbKnot<NV, NC> k;
   float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+  WbCostSmem<NV, NC> cs;
   float prim[NT / 32][MAXD * WB_SLOT];
   float tan[MAXD * WB_SLOT * NDS];
 };
@@ -148,79 +365,100 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
 
-  // ---- P5: cost value + gradient (forward mode, one direction per thread per pass)
-  for (int d = tid; d < n + m; d += NT) {
-    if (term && d >= n) break;
-    Dual x[NX], u[NU];
-    for (int i = 0; i < n; ++i) x[i] = Dual(sx[i], i == d ? 1.f : 0.f);
-    for (int i = 0; i < m; ++i) u[i] = Dual(su[i], n + i == d ? 1.f : 0.f);
-    const Dual cst = wb_cost<Dual, NJ, NC>(md, W, ref, x, u, term);
-    sgrad[d] = cst.d;
-    if (d == 0) o.cost[size_t(e) * (N + 1) + t] = cst.v;
-  }
-  if (tid < 4) {
-    Dual q[4], rs[3];
-    for (int i = 0; i < 4; ++i) q[i] = Dual(sx[3 + i], i == tid ? 1.f : 0.f);
-    quat_sub(q, ref + 3, rs);
-    for (int k = 0; k < 3; ++k) sG[k * 4 + tid] = rs[k].d;
-  }
-  __syncthreads();
-  // q_t = grad_x cost + A^T V_{t+1} - V_t ; r_t = grad_u cost + B^T V_{t+1}   (optimizers.py:111-120,165-169)
-  for (int i = tid; i < n; i += NT) o.q[(size_t(e) * (N + 1) + t) * n + i] = sgrad[i] + satv[i] - Vt[i];
-  if (!term)
-    for (int i = tid; i < m; i += NT) o.r[(size_t(e) * N + t) * m + i] = sgrad[n + i] + satv[n + i];
+  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sgrad, satv, sG, sm.cs);
+}
 
-  // ---- Gauss-Newton blocks Q = Jx^T W Jx (+ penalty curvature), R, M   (objectives.py:127-202, 252-323, 378-450)
-  const int nw = md.nw, nf = 3 * nc;
-  const float* contact = ref + 13 + nj + nf;
-  const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
-  float* Q = o.Q + (size_t(e) * (N + 1) + t) * n * n;
-  for (int idx = tid; idx < n * n; idx += NT) {
-    const int i = idx / n, j = idx - i * n;
-    const WbResMap ri = wb_resmap_x(md, i, sG, contact), rj = wb_resmap_x(md, j, sG, contact);
-    float s = 0.f;
-    for (int a = 0; a < ri.cnt; ++a)
-      for (int b = 0; b < rj.cnt; ++b) s = fmaf(ri.c[a] * rj.c[b], W[ri.a[a] * nw + rj.a[b]], s);
-    if (md.kind == MPXB_KIND_QUAD_WB) {
-      const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
-      if (i >= g0 && j >= g0 && (i - g0) / 3 == (j - g0) / 3) {
-        // friction cone curvature: eps = 1e-1 here (objectives.py:167), clip +-1e6, masked by contact
-        const int c = (i - g0) / 3;
-        const float gx = sx[g0 + 3 * c], gy = sx[g0 + 3 * c + 1], gz = sx[g0 + 3 * c + 2];
-        const float sq = sqrtf(gy * gy + gx * gx + 1e-1f);
-        const float h = fminf(fmaxf(penalty_dd(0.5f * gz - sq, 0.1f, 5.f), -1e6f), 1e6f) * contact[c];
-        const float jf[3] = {-gx / sq, -gy / sq, 0.5f};
-        s = fmaf(h * jf[i - g0 - 3 * c], jf[j - g0 - 3 * c], s);
-      }
-      if (i == j && i >= v0 && i < v0 + nj) {
-        const float dq = sx[i];
-        s += fminf(fmaxf(penalty_dd(10.01f - dq, 0.1f, 5.f), -1e6f), 1e6f) +
-             fminf(fmaxf(penalty_dd(dq + 10.01f, 0.1f, 5.f), -1e6f), 1e6f);
-      }
-    }
-    Q[idx] = s;
+// ---------------------------------------------------------------------------------------------------------------
+// Linearise kernel v3: per-body tree quantities in shared memory + analytic derivatives (wb_tree.cuh).
+//   S1  leaf-path workers: kinematics, joint motion vectors, spatial velocities / bias accelerations
+//   S2  body workers: spatial inertia, momentum, bias force, foot offsets         S3  composites (component workers)
+//   S4  dof workers: U_i, qfrc_bias ; pair workers: qM, foot Jacobians
+//   P2  cooperative contact solve (as v2)                                          S5  acceleration problems w, a, z
+//   S6  (direction, body) force perturbations + subtree sums
+//   S7  thread d: folded tangents of direction d (analytic) -> column d of [A | B] (wb_s3_tangent), A'V / B'V
+//   P5  cost gradient, q, r, Gauss-Newton blocks
+template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
+  static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
+  WbKnot<NV, NC> k;
+  WbTree<NB, NV, NC, NI> tr;
+  WbCostSmem<NV, NC> cs;
+  float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+};
+
+template <int NB, int NV, int NC, int NI, int NT>
+__global__ void __launch_bounds__(NT) wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
+  using S = WbLin3Smem<NB, NV, NC, NI, NT>;
+  constexpr int NDS = S::NDS, NQ = NV + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const WbModel& md = *mdp;
+  const int tid = threadIdx.x;
+  const int N = io.N;
+  const int e = blockIdx.x / (N + 1), t = blockIdx.x - e * (N + 1);
+  if (io.done && io.done[e]) return;
+  const int n = md.n, m = md.m;
+  const bool term = (t == N);
+  const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
+  const float* Ut = io.U + (size_t(e) * N + t) * m;
+  const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+  const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
+  float* sx = sm.sx;
+  float* su = sm.su;
+  float* svn = sm.svn;
+  float* satv = sm.satv;
+  for (int i = tid; i < n; i += NT) {
+    sx[i] = Xt[i];
+    svn[i] = term ? 0.f : Vt[n + i];
+    satv[i] = 0.f;
   }
+  for (int i = tid; i < m; i += NT) { su[i] = term ? 0.f : Ut[i]; satv[n + i] = 0.f; }
+  __syncthreads();
+
   if (!term) {
-    float* M = o.M + (size_t(e) * N + t) * n * m;
-    for (int idx = tid; idx < n * m; idx += NT) {
-      const int i = idx / m, j = idx - i * m;
-      const WbResMap ri = wb_resmap_x(md, i, sG, contact);
-      float s = 0.f;
-      for (int a = 0; a < ri.cnt; ++a) s = fmaf(ri.c[a], W[ri.a[a] * nw + ua0 + j], s);
-      M[idx] = s;
+    auto sync = [] { __syncthreads(); };
+    wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, NT);
+    __syncthreads();
+    wb_tree_bodies(md, sm.tr, sx, sm.k.feet, tid, NT);
+    __syncthreads();
+    wb_tree_composite(md, sm.tr, tid, NT);
+    __syncthreads();
+    wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
+    __syncthreads();
+    wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
+    __syncthreads();
+    wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
+    {
+      float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
+      const float* Xn = Xt + n;
+      for (int i = tid; i < n; i += NT) c[i] = sm.k.xn[i] - Xn[i];
     }
-    float* R = o.R + (size_t(e) * N + t) * m * m;
-    for (int idx = tid; idx < m * m; idx += NT) {
-      const int i = idx / m, j = idx - i * m;
-      float s = W[(ua0 + i) * nw + ua0 + j];
-      if (md.kind == MPXB_KIND_QUAD_WB && i == j && i < nj) {
-        const float tq = su[i];
-        s += fminf(fmaxf(penalty_dd(44.01f - tq, 1.f, 1.f), -1e6f), 1e6f) +
-             fminf(fmaxf(penalty_dd(tq + 44.01f, 1.f, 1.f), -1e6f), 1e6f);
-      }
-      R[idx] = s;
+    wb_tree_acc(md, sm.tr, sm.k.w, sm.k.a, sm.k.z, tid, NT, sync);
+    __syncthreads();
+    wb_tree_items(md, sm.tr, tid, NT, sync);
+    __syncthreads();
+    float* A = o.A + (size_t(e) * N + t) * n * n;
+    float* B = o.B + (size_t(e) * N + t) * n * m;
+    if (tid < NDS + m) {
+      float t1[NV], t2[NV], ee[NV], hh[3 * NC], dfeet[3 * NC];
+      const int is_u = tid >= NDS;
+      if (!is_u)
+        wb_tree_fold(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, tid, t1, t2, ee, hh, dfeet);
+      float atv = 0.f;
+      float* dst = is_u ? B + (tid - NDS) : A + tid;
+      const int ld = is_u ? m : n;
+      wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet,
+                            [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); });
+      satv[is_u ? n + tid - NDS : tid] = atv;
+    }
+    const int ntail = n - NDS;
+    for (int idx = tid; idx < n * ntail; idx += NT) {
+      const int i = idx / ntail, j = NDS + idx - i * ntail;
+      A[i * n + j] = 0.f;
     }
   }
+  if (t == 0)
+    for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
+  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sm.sgrad, satv, sm.sG, sm.cs);
 }
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
@@ -302,8 +540,30 @@ inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const Mod
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
-// tree classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u]
+template <int NB, int NV, int NC, int NI, int NT>
+inline int wb_launch_linearize3_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
+  using S = WbLin3Smem<NB, NV, NC, NI, NT>;
+  auto kern = wb_linearize3_kernel<NB, NV, NC, NI, NT>;
+  static bool configured[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 64 && !configured[d]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
+    configured[d] = true;
+  }
+  kern<<<io.E * (io.N + 1), NT, sizeof(S), st>>>(dev, io, lo);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
+// tree classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u].
+// v3 (analytic derivatives) whenever the model's tables fit; MPXB_WB_LINEARIZE=2 forces the forward-mode v2 kernel.
 inline int wb_launch_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
+  static const int force_v2 = [] { const char* v = getenv("MPXB_WB_LINEARIZE"); return (v && v[0] == '2') ? 1 : 0; }();
+  if (h.tree_ok && !force_v2) {
+    if (h.nv == 18 && h.nc == 4 && h.nbody <= 14 && h.nitems <= 192) return wb_launch_linearize3_t<14, 18, 4, 192, 64>(h, dev, io, lo, st);
+    if (h.nv == 25 && h.nc == 4 && h.nbody <= 21 && h.nitems <= 320) return wb_launch_linearize3_t<21, 25, 4, 320, 96>(h, dev, io, lo, st);
+    if (h.nv == 28 && h.nc == 8 && h.nbody <= 32 && h.nitems <= 640) return wb_launch_linearize3_t<32, 28, 8, 640, 128>(h, dev, io, lo, st);
+  }
   if (h.nv == 18 && h.nc == 4) return wb_launch_linearize_t<18, 4, 4, 64>(h, dev, io, lo, st);
   if (h.nv == 25 && h.nc == 4) return wb_launch_linearize_t<25, 4, 6, 96>(h, dev, io, lo, st);
   if (h.nv == 28 && h.nc == 8) return wb_launch_linearize_t<28, 8, 10, 128>(h, dev, io, lo, st);

@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libharness.so")
 
 def build(force=False):
     srcs = [os.path.join(HERE, "harness.cpp")] + [os.path.join(ROOT, "mpx_b200", "csrc", f)
-                                                   for f in ("common.cuh", "srbd.cuh", "wb.cuh")]
+                                                   for f in ("common.cuh", "srbd.cuh", "wb.cuh", "wb_tree.cuh")]
     srcs.append(os.path.join(ROOT, "include", "mpxb.h"))
     if not force and os.path.exists(OUT) and all(os.path.getmtime(s) <= os.path.getmtime(OUT) for s in srcs):
         return OUT

@@ -5,6 +5,7 @@
 
 #include "../../mpx_b200/csrc/srbd.cuh"
 #include "../../mpx_b200/csrc/wb.cuh"
+#include "../../mpx_b200/csrc/wb_tree.cuh"
 
 using namespace mpxb;
 
@@ -77,9 +78,67 @@ void hybrid_t(const WbModel& md, const float* x, const float* u, const float* co
     for (int j = nq + nv; j < n; ++j) A[i * n + j] = 0.f;
 }
 
+// x+ and [A | B] through the v3 path of the linearise kernel: per-body tree quantities (wb_tree_*), the cooperative
+// contact solve, ANALYTIC folded tangents (wb_tree_fold) and wb_s3_tangent.  One worker.
+template <int NB, int NV, int NC, int NI>
+int tree_t(const WbModel& md, const float* x, const float* u, const float* contact, float* xn, float* A, float* B) {
+  const int n = md.n, m = md.m, nj = md.nj, nv = md.nv, nq = 7 + nj;
+  if (!md.tree_ok || md.nitems > NI) return -3;
+  static WbKnot<NV, NC> k;
+  static WbTree<NB, NV, NC, NI> tr;
+  auto nosync = [] {};
+  const float* qpos = x;
+  const float* qvel = x + nq;
+  wb_tree_fk(md, tr, qpos, qvel, 0, 1);
+  wb_tree_bodies(md, tr, qpos, k.feet, 0, 1);
+  wb_tree_composite(md, tr, 0, 1);
+  wb_tree_dofs(md, tr, k.D, 0, 1);
+  wb_tree_mass_jac(md, tr, k.M, k.J, 0, 1);
+  wb_s3_primal<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
+  for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
+  wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
+  wb_tree_items(md, tr, 0, 1, nosync);
+  std::vector<float> col(n);
+  for (int d = 0; d < nq + nv + m; ++d) {
+    float t1[NV] = {0}, t2[NV] = {0}, e[NV] = {0}, h[3 * NC] = {0}, dfeet[3 * NC] = {0};
+    const int is_u = d >= nq + nv;
+    if (!is_u) wb_tree_fold(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, d, t1, t2, e, h, dfeet);
+    float* cp = col.data();
+    wb_s3_tangent<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
+                          [cp](int i, float v) { cp[i] = v; });
+    for (int i = 0; i < n; ++i) {
+      if (!is_u) A[i * n + d] = col[i];
+      else B[i * m + d - nq - nv] = col[i];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = nq + nv; j < n; ++j) A[i * n + j] = 0.f;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int h_wb_dynamics_tree(const mpxb_model_desc* d, const float* x, const float* u, const float* contact, float* xn,
+                       float* A, float* B) {
+  WbModel md;
+  int rc = wb_build_model(*d, &md);
+  if (rc) return rc;
+  if (md.nv == 18 && md.nc == 4) return tree_t<14, 18, 4, 192>(md, x, u, contact, xn, A, B);
+  if (md.nv == 25 && md.nc == 4) return tree_t<21, 25, 4, 320>(md, x, u, contact, xn, A, B);
+  if (md.nv == 28 && md.nc == 8) return tree_t<32, 28, 8, 640>(md, x, u, contact, xn, A, B);
+  return -2;
+}
+
+// tables of the analytic linearisation, for inspection
+int h_wb_tree_info(const mpxb_model_desc* d, int* out) {
+  WbModel md;
+  int rc = wb_build_model(*d, &md);
+  if (rc) return rc;
+  out[0] = md.tree_ok; out[1] = md.nleaf; out[2] = md.ndir; out[3] = md.nitems; out[4] = md.maxdepth;
+  return 0;
+}
 
 // x+ = f(x, u) and (optionally) A = df/dx [n,n], B = df/du [n,m] by forward mode, as the linearise kernel does
 int h_wb_dynamics(const mpxb_model_desc* d, const float* x, const float* u, const float* contact, float* xn, float* A,

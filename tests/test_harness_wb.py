@@ -90,7 +90,7 @@ def test_mjx_terms(H, robot, fn):
     assert abs(M[0, 0] - pr.robot_mass) / pr.robot_mass < 1e-5
 
 
-@pytest.mark.parametrize("fn", ["h_wb_dynamics", "h_wb_dynamics_hybrid"])
+@pytest.mark.parametrize("fn", ["h_wb_dynamics", "h_wb_dynamics_hybrid", "h_wb_dynamics_tree"])
 @pytest.mark.parametrize("contact_pattern", ["all", "trot"])
 def test_dynamics_and_jacobians(H, robot, contact_pattern, fn):
     """x+ = f(x,u), A = df/dx, B = df/du: plain forward mode through the whole dynamics (h_wb_dynamics) and the
