@@ -15,7 +15,7 @@
 #include "lq.cuh"
 #include "sqp.cuh"
 #include "srbd_kernels.cuh"
-#include "wb_kernels.cuh"
+#include "wb_launch.h"
 #include "lq_scan.cuh"
 #include "refgen.cuh"
 

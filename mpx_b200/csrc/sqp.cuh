@@ -2,12 +2,12 @@
 // filter line-search decision + iterate update + convergence bookkeeping (optimizers.py:468-578,
 // mpc_wrapper.py:456-467) and the warm-start shift (mpc_wrapper.py:79-98).
 #pragma once
+#include "model_io.cuh"
 #include <cuda_runtime.h>
 #include "common.cuh"
 
 namespace mpxb {
 
-constexpr int NALPHA = 11;  // alpha_values = exp2(-arange(11))  (optimizers.py:518)
 
 // Offsets (in floats) of each per-batch array inside the caller's workspace.
 struct WsLayout {

@@ -3,22 +3,11 @@
 // Reference: optimizers.py:580-602 (model_evaluator), 150-173 (linearize / hessian_approx / lagrangian),
 // 518-540 (trial points); models.py:6-37; objectives.py:15-75.
 #pragma once
+#include "model_io.cuh"
 #include "srbd.cuh"
 #include "sqp.cuh"
 
 namespace mpxb {
-
-struct ModelIO {
-  int E, N;
-  const float *reference, *parameter, *W;
-  size_t w_stride;  // floats between consecutive envs' W (0 = shared)
-  const float *x0, *X, *U, *V;
-  const int32_t* done;
-};
-
-struct LinOut {
-  float *A, *B, *Q, *R, *M, *q, *r, *c, *cost;
-};
 
 // grid: ceil(E*(N+1) / (blockDim/32)) ; one warp per (env, knot)
 __global__ void srbd_linearize_kernel(SrbdParams P, ModelIO io, LinOut o) {
@@ -126,11 +115,6 @@ __global__ void srbd_linearize_kernel(SrbdParams P, ModelIO io, LinOut o) {
     }
   }
 }
-
-struct TrialOut {
-  const float *dX, *dU;
-  float *ls_theta, *ls_phi;
-};
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
 __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {

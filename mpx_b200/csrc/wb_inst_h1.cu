@@ -1,0 +1,16 @@
+// wb_inst_h1.cu -- whole-body kernels instantiated for the "h1" tree class (nbody <= 21, nv = 25, nc = 4).
+#include <cuda_runtime.h>
+
+#include "wb_kernels.cuh"
+#include "wb_launch.h"
+
+namespace mpxb {
+
+int wb_h1_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st, int force_v2) {
+  return wb_class_linearize<21, 25, 4, 6, 320, 96>(h, dev, io, lo, st, force_v2);
+}
+int wb_h1_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
+  return wb_class_trial<21, 25, 4>(h, dev, io, to, st);
+}
+
+}  // namespace mpxb

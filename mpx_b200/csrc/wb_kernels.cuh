@@ -8,7 +8,7 @@
 // the residual map (identity except the 3x4 quaternion-error Jacobian) and the penalty curvatures.
 #pragma once
 #include "../../include/mpxb.h"
-#include "srbd_kernels.cuh"
+#include "model_io.cuh"
 #include "wb.cuh"
 #include "wb_tree.cuh"
 #include <stdlib.h>
@@ -555,27 +555,19 @@ inline int wb_launch_linearize3_t(const WbModel& h, const WbModel* dev, const Mo
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
-// tree classes: quadrupeds (aliengo, go2), H1, Talos; one thread per direction of [qpos | qvel | u].
-// v3 (analytic derivatives) whenever the model's tables fit; MPXB_WB_LINEARIZE=2 forces the forward-mode v2 kernel.
-inline int wb_launch_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
-  static const int force_v2 = [] { const char* v = getenv("MPXB_WB_LINEARIZE"); return (v && v[0] == '2') ? 1 : 0; }();
-  if (h.tree_ok && !force_v2) {
-    if (h.nv == 18 && h.nc == 4 && h.nbody <= 14 && h.nitems <= 192) return wb_launch_linearize3_t<14, 18, 4, 192, 64>(h, dev, io, lo, st);
-    if (h.nv == 25 && h.nc == 4 && h.nbody <= 21 && h.nitems <= 320) return wb_launch_linearize3_t<21, 25, 4, 320, 96>(h, dev, io, lo, st);
-    if (h.nv == 28 && h.nc == 8 && h.nbody <= 32 && h.nitems <= 640) return wb_launch_linearize3_t<32, 28, 8, 640, 128>(h, dev, io, lo, st);
-  }
-  if (h.nv == 18 && h.nc == 4) return wb_launch_linearize_t<18, 4, 4, 64>(h, dev, io, lo, st);
-  if (h.nv == 25 && h.nc == 4) return wb_launch_linearize_t<25, 4, 6, 96>(h, dev, io, lo, st);
-  if (h.nv == 28 && h.nc == 8) return wb_launch_linearize_t<28, 8, 10, 128>(h, dev, io, lo, st);
-  return MPXB_EUNSUPPORTED;
+// One robot class = one translation unit (wb_inst_quad.cu / wb_inst_h1.cu / wb_inst_talos.cu) so the classes compile
+// in parallel.  v3 (analytic derivatives) whenever the model's tables fit; force_v2 selects the forward-mode kernel.
+template <int NB, int NV, int NC, int MAXD, int NI, int NT>
+inline int wb_class_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st,
+                              int force_v2) {
+  if (h.tree_ok && !force_v2 && h.nbody <= NB && h.nitems <= NI) return wb_launch_linearize3_t<NB, NV, NC, NI, NT>(h, dev, io, lo, st);
+  return wb_launch_linearize_t<NV, NC, MAXD, NT>(h, dev, io, lo, st);
 }
-
-inline int wb_launch_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
+template <int NB, int NV, int NC>
+inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
   const int wpb = 2;
   const int blocks = (io.E * NALPHA + wpb - 1) / wpb;
-  if (h.nbody <= 14 && h.nv <= 18 && h.nc <= 4) wb_trial_kernel<14, 18, 4><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
-  else if (h.nbody <= 21 && h.nv <= 25 && h.nc <= 4) wb_trial_kernel<21, 25, 4><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
-  else wb_trial_kernel<32, 28, 8><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+  wb_trial_kernel<NB, NV, NC><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
