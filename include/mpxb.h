@@ -102,6 +102,15 @@ typedef struct mpxb_model mpxb_model; /* opaque; owns its constant device tables
 int mpxb_model_create(const mpxb_model_desc* desc, mpxb_model** out);
 void mpxb_model_destroy(mpxb_model* model);
 
+/* Options of a model handle (set before the first mpxb_mpc_step; not thread-safe against a running call).
+ * MPXB_OPT_EAGER_LINE_SEARCH (default 0): the reference evaluates all 11 trial points of the filter line search
+ * in one vmap and keeps the first accepted one (optimizers.py:518-572).  By default libmpxb evaluates alpha = 1
+ * first and the ten smaller steps only for environments whose alpha = 1 point is rejected -- X, U, V and
+ * alpha_index are identical, but the workspace views "ls_theta" / "ls_phi" then hold entries 1..10 only for
+ * those environments.  Set to 1 to evaluate all 11 points for every environment (diagnostics / parity tests). */
+enum { MPXB_OPT_EAGER_LINE_SEARCH = 1 };
+int mpxb_model_set_option(mpxb_model* model, int option, int value);
+
 /* Bytes of device scratch one mpxb_mpc_step call with E environments needs. */
 size_t mpxb_workspace_bytes(const mpxb_model* model, int E, int lq_mode);
 

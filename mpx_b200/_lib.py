@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libmpxb.so")
 
 MAX_BODY, MAX_DOF, MAX_CONTACT = 32, 32, 8
 KIND_SRBD, KIND_QUAD_WB, KIND_H1_WB, KIND_TALOS_WB = 0, 1, 2, 3
+OPT_EAGER_LINE_SEARCH = 1
 LQ_SEQUENTIAL, LQ_SCAN = 0, 1
 ERRORS = {0: "ok", -1: "MPXB_EINVAL", -2: "MPXB_EUNSUPPORTED", -3: "MPXB_EWORKSPACE", -4: "MPXB_ECUDA"}
 
@@ -56,6 +57,8 @@ def lib():
     L.mpxb_version_string.restype = C.c_char_p
     L.mpxb_model_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp)]
     L.mpxb_model_create.restype = i32
+    L.mpxb_model_set_option.argtypes = [vp, i32, i32]
+    L.mpxb_model_set_option.restype = i32
     L.mpxb_model_destroy.argtypes = [vp]
     L.mpxb_model_destroy.restype = None
     L.mpxb_workspace_bytes.argtypes = [vp, i32, i32]

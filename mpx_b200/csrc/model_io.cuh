@@ -24,6 +24,57 @@ struct LinOut {
 struct TrialOut {
   const float *dX, *dU;
   float *ls_theta, *ls_phi;
+  // lazy filter line search: the launch covers trial points ia0 .. ia0+nia-1.  The warp of trial point 0 also
+  // reduces theta_k = sum c^2 and phi_k = sum cost of the CURRENT iterate and records whether alpha = 1 is rejected
+  // (need[e]); a launch with ia0 > 0 skips every environment whose need flag is clear.
+  const float *c, *cost, *slope;
+  float *theta_k, *phi_k;
+  int32_t* need;
+  int ia0, nia;
 };
+
+#if defined(__CUDACC__)
+// The 3-case filter acceptance test of parallel_filter_line_search (optimizers.py:541-566) with JAX's NaN semantics
+__device__ __forceinline__ bool filter_accept(float theta_new, float phi_new, float theta_k, float phi_k, float slope,
+                                              float alpha) {
+  const float theta_max = 1e-2f, theta_min = 1e-6f, eta = 1e-4f, gamma_phi = 1e-6f, gamma_theta = 1e-6f;
+  const bool cond1 = theta_new > theta_max;
+  const bool case1 = cond1 && (theta_new < (1.f - gamma_theta) * theta_k);
+  const bool cond2 = (fmaxf(theta_new, theta_k) < theta_min) && (slope < 0.f);
+  // jnp.maximum propagates NaN; fmaxf does not -> test explicitly
+  const bool cond2n = cond2 && !(theta_new != theta_new) && !(theta_k != theta_k);
+  const bool case2 = cond2n && (phi_new < phi_k + eta * alpha * slope);
+  const bool cond3 = !(cond1 || cond2n);
+  const bool case3 = cond3 && ((phi_new < phi_k - gamma_phi * phi_k) || (theta_new < (1.f - gamma_theta) * theta_k));
+  return case1 || case2 || case3;
+}
+
+// Tail of the trial kernels (one warp per (env, trial point)): store theta / phi; trial point 0 adds theta_k, phi_k
+// of the current iterate (fixed-order warp reduction: deterministic) and the lazy-evaluation flag.
+__device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& o, int e, int ia, int lane, int n,
+                                             float theta, float phi) {
+  if (lane == 0) {
+    o.ls_theta[e * NALPHA + ia] = theta;
+    o.ls_phi[e * NALPHA + ia] = phi;
+  }
+  if (ia != 0) return;
+  const int N = io.N;
+  const size_t nx = size_t(N + 1) * n;
+  const float* c = o.c + size_t(e) * nx;
+  float th = 0.f, ph = 0.f;
+  for (size_t i = lane; i < nx; i += 32) th = fmaf(c[i], c[i], th);
+  for (int t = lane; t <= N; t += 32) ph += o.cost[size_t(e) * (N + 1) + t];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    th += __shfl_xor_sync(0xffffffffu, th, s);
+    ph += __shfl_xor_sync(0xffffffffu, ph, s);
+  }
+  if (lane == 0) {
+    o.theta_k[e] = th;
+    o.phi_k[e] = ph;
+    if (o.need) o.need[e] = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
+  }
+}
+#endif
 
 }  // namespace mpxb

@@ -31,6 +31,7 @@ struct mpxb_model {
   mpxb_profile* prof;
   SrbdParams srbd;
   WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
+  int eager_line_search;  // 1: evaluate all 11 trial points every call (default 0: lazy, same result)
   WbModel wb_host;
   int device;
 };
@@ -99,6 +100,7 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   mdl->desc = *d;
   mdl->wb_dev = nullptr;
   mdl->prof = nullptr;
+  mdl->eager_line_search = 0;
   cudaGetDevice(&mdl->device);
   if (d->kind == MPXB_KIND_SRBD) {
     if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
@@ -121,6 +123,12 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   }
   *out = mdl;
   return MPXB_OK;
+}
+
+int mpxb_model_set_option(mpxb_model* m, int option, int value) {
+  if (!m) return MPXB_EINVAL;
+  if (option == MPXB_OPT_EAGER_LINE_SEARCH) { m->eager_line_search = value ? 1 : 0; return MPXB_OK; }
+  return MPXB_EINVAL;
 }
 
 void mpxb_model_destroy(mpxb_model* m) {
@@ -167,7 +175,9 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     float* Vn = to_user ? V : ws + L.Vt;
     ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
     LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost};
-    TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi};
+    int32_t* need = reinterpret_cast<int32_t*>(ws + L.need);
+    TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi, ws + L.c, ws + L.cost, ws + L.slope,
+                ws + L.theta_k, ws + L.phi_k, need, 0, NALPHA};
     mpxb_profile* pf = (it == max_iter - 1 && mdl->prof && mdl->prof->calls < mdl->prof->max_calls) ? mdl->prof : nullptr;
     cudaEvent_t* pev = pf ? pf->ev + 5 * pf->calls : nullptr;
     if (pev) cudaEventRecord(pev[0], st);
@@ -188,18 +198,25 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
                                              : dispatch_lq_scan(n, m, la, ws + L.scan, st);
     if (rc != MPXB_OK) return rc;
     if (pev) cudaEventRecord(pev[2], st);
-    // K3
-    if (d.kind == MPXB_KIND_SRBD) {
-      const int wpb = 4;
-      const int blocks = (E * NALPHA + wpb - 1) / wpb;
-      srbd_trial_kernel<<<blocks, wpb * 32, 0, st>>>(mdl->srbd, io, to);
-    } else {
-      rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, io, to, st);
-      if (rc != MPXB_OK) return rc;
+    // K3: the 11 trial points.  Lazy (default): alpha = 1 first; the ten smaller steps only for the environments
+    // whose alpha = 1 point the filter rejects -- the first accepted point is all the reference keeps
+    // (optimizers.py:568-572), so X, U, V and alpha_index are unchanged.
+    const int npass = mdl->eager_line_search ? 1 : 2;
+    for (int pass = 0; pass < npass; ++pass) {
+      if (mdl->eager_line_search) { to.ia0 = 0; to.nia = NALPHA; to.need = nullptr; }
+      else { to.ia0 = pass; to.nia = pass == 0 ? 1 : NALPHA - 1; }
+      if (d.kind == MPXB_KIND_SRBD) {
+        const int wpb = 4;
+        const int blocks = (E * to.nia + wpb - 1) / wpb;
+        srbd_trial_kernel<<<blocks, wpb * 32, 0, st>>>(mdl->srbd, io, to);
+      } else {
+        rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, io, to, st);
+        if (rc != MPXB_OK) return rc;
+      }
     }
     if (pev) cudaEventRecord(pev[3], st);
     // K4
-    SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.cost, ws + L.c, ws + L.ls_theta,
+    SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.theta_k, ws + L.phi_k, ws + L.ls_theta,
                   ws + L.ls_phi, ws + L.slope, Xn, Un, Vn, ws + L.g, ws + L.last_cost, done, alpha_index, iters,
                   status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0};
     select_update_kernel<<<E, 128, 0, st>>>(sa);

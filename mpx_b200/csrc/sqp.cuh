@@ -12,7 +12,7 @@ namespace mpxb {
 // Offsets (in floats) of each per-batch array inside the caller's workspace.
 struct WsLayout {
   size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
-      done, scan, total;
+      done, scan, theta_k, phi_k, need, total;
 };
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
@@ -48,6 +48,9 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
   L.last_cost = take(e);
   L.done = take(e);  // int32
   L.scan = take(scan_floats);
+  L.theta_k = take(e);
+  L.phi_k = take(e);
+  L.need = take(e);  // int32
   L.total = o;
   return L;
 }
@@ -55,7 +58,7 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
 struct SelectArgs {
   int E, N, n, m;
   const float *X_in, *U_in, *V_in, *dX, *dU, *dV;
-  const float *cost, *c, *ls_theta, *ls_phi, *slope;
+  const float *theta_k, *phi_k, *ls_theta, *ls_phi, *slope;  // theta_k / phi_k: written by the trial kernel
   float *X, *U, *V;
   float* g_out;
   float* last_cost;      // per env, offline stopping rule state (may be null)
@@ -81,39 +84,20 @@ __global__ void select_update_kernel(SelectArgs a) {
     for (size_t i = tid; i < nu; i += blockDim.x) Uo[i] = Ui[i];
     return;
   }
-  __shared__ float s_red[2][32];
   __shared__ int s_idx;
   __shared__ float s_alpha;
-  // theta_k = sum c^2 , phi_k = sum_t cost_t  (fixed-order block reduction: deterministic)
-  float th = 0.f, ph = 0.f;
-  const float* c = a.c + e * nx;
-  for (size_t i = tid; i < nx; i += blockDim.x) th = fmaf(c[i], c[i], th);
-  for (int t = tid; t <= N; t += blockDim.x) ph += a.cost[size_t(e) * (N + 1) + t];
-  for (int o = 16; o > 0; o >>= 1) {
-    th += __shfl_xor_sync(0xffffffffu, th, o);
-    ph += __shfl_xor_sync(0xffffffffu, ph, o);
-  }
-  if ((tid & 31) == 0) { s_red[0][tid >> 5] = th; s_red[1][tid >> 5] = ph; }
-  __syncthreads();
   if (tid == 0) {
-    float theta_k = 0.f, phi_k = 0.f;
-    for (int w = 0; w < int(blockDim.x >> 5); ++w) { theta_k += s_red[0][w]; phi_k += s_red[1][w]; }
+    // theta_k = sum c^2, phi_k = sum_t cost_t of the current iterate (reduced by the trial kernel)
+    const float theta_k = a.theta_k[e], phi_k = a.phi_k[e];
     const float slope = a.slope[e];
-    const float theta_max = 1e-2f, theta_min = 1e-6f, eta = 1e-4f, gamma_phi = 1e-6f, gamma_theta = 1e-6f;
-    int best = NALPHA - 1;  // index -1 of the 11 trials when none is accepted (optimizers.py:572)
-    for (int i = NALPHA - 1; i >= 0; --i) {
-      const float alpha = exp2f(-float(i));
-      const float theta_new = a.ls_theta[e * NALPHA + i];
-      const float phi_new = a.ls_phi[e * NALPHA + i];
-      const bool cond1 = theta_new > theta_max;
-      const bool case1 = cond1 && (theta_new < (1.f - gamma_theta) * theta_k);
-      const bool cond2 = (fmaxf(theta_new, theta_k) < theta_min) && (slope < 0.f);
-      // jnp.maximum propagates NaN; fmaxf does not -> test explicitly
-      const bool cond2n = cond2 && !(theta_new != theta_new) && !(theta_k != theta_k);
-      const bool case2 = cond2n && (phi_new < phi_k + eta * alpha * slope);
-      const bool cond3 = !(cond1 || cond2n);
-      const bool case3 = cond3 && ((phi_new < phi_k - gamma_phi * phi_k) || (theta_new < (1.f - gamma_theta) * theta_k));
-      if (case1 || case2 || case3) best = i;  // descending loop keeps the smallest accepted index
+    // first accepted trial point (largest alpha), else index -1 of the 11 trials (optimizers.py:568-572).  Ascending
+    // with early exit: when the line search ran lazily the entries behind the first accepted one were never evaluated.
+    int best = NALPHA - 1;
+    for (int i = 0; i < NALPHA; ++i) {
+      if (filter_accept(a.ls_theta[e * NALPHA + i], a.ls_phi[e * NALPHA + i], theta_k, phi_k, slope, exp2f(-float(i)))) {
+        best = i;
+        break;
+      }
     }
     s_idx = best;
     s_alpha = exp2f(-float(best));

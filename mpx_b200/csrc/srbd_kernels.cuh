@@ -122,9 +122,10 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int N = io.N;
-  if (warp >= io.E * NALPHA) return;
-  const int e = warp / NALPHA, ia = warp - e * NALPHA;
+  if (warp >= io.E * o.nia) return;
+  const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
   if (io.done && io.done[e]) return;
+  if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
   const float alpha = exp2f(-float(ia));
   const float* W = io.W + size_t(e) * io.w_stride;
   float theta = 0.f, phi = 0.f;
@@ -168,10 +169,7 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
     theta += __shfl_xor_sync(0xffffffffu, theta, s);
     phi += __shfl_xor_sync(0xffffffffu, phi, s);
   }
-  if (lane == 0) {
-    o.ls_theta[e * NALPHA + ia] = theta;
-    o.ls_phi[e * NALPHA + ia] = phi;
-  }
+  trial_finish(io, o, e, ia, lane, n, theta, phi);
 }
 
 }  // namespace mpxb

@@ -186,13 +186,13 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
 
   // ---- Gauss-Newton blocks Q = Jx^T W Jx (+ penalty curvature), R, M   (objectives.py:127-202, 252-323, 378-450)
   float* Q = o.Q + (size_t(e) * (N + 1) + t) * n * n;
+  // columns of the identity-mapped state entries: Q[i][j] = c_i c_j W[a_i][a_j], rows walked block by block
   for (int j = tid; j < n; j += NT) {
     const int aj = cs.ra[j];
+    if (aj < 0) continue;  // quaternion columns: below
     const float cj = cs.rc[j];
-    const bool jq = aj < 0;
-    float gq[3] = {0.f, 0.f, 0.f};
-    if (jq) { gq[0] = sG[j - 3]; gq[1] = sG[4 + j - 3]; gq[2] = sG[8 + j - 3]; }
-    // W column(s) of j folded with the quaternion map: wj(a) = sum_b W[a][b] (dr_b / dx_j)
+    const float* Wc = W + aj;
+    float* Qc = Q + j;
     float curv_speed = 0.f;
     if (quad && j >= v0 && j < v0 + nj) {
       const float dq = sx[j];
@@ -209,26 +209,38 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
       jf3[0] = -gx / sq; jf3[1] = -gy / sq; jf3[2] = 0.5f;
       jfj = jf3[j - g0 - 3 * cj_foot];
     }
-    for (int i = 0; i < n; ++i) {
-      const int ai = cs.ra[i];
-      float s;
-      if (ai >= 0) {
-        const float ci = cs.rc[i];
-        if (!jq) s = ci * cj * W[ai * nw + aj];
-        else s = ci * (gq[0] * W[ai * nw + 3] + gq[1] * W[ai * nw + 4] + gq[2] * W[ai * nw + 5]);
-      } else {
-        s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float gi = sG[k * 4 + i - 3];
-          if (!jq) s = fmaf(gi * cj, W[(3 + k) * nw + aj], s);
-          else s = fmaf(gi, gq[0] * W[(3 + k) * nw + 3] + gq[1] * W[(3 + k) * nw + 4] + gq[2] * W[(3 + k) * nw + 5], s);
-        }
-      }
-      if (cj_foot >= 0 && i >= g0 && (i - g0) / 3 == cj_foot) s = fmaf(hcone * jf3[i - g0 - 3 * cj_foot], jfj, s);
-      if (i == j) s += curv_speed;
-      Q[i * n + j] = s;
+    for (int i = 0; i < 3; ++i) Qc[i * n] = cj * Wc[i * nw];
+    {
+      const float w3 = cj * Wc[3 * nw], w4 = cj * Wc[4 * nw], w5 = cj * Wc[5 * nw];
+      for (int i = 3; i < 7; ++i) Qc[i * n] = sG[i - 3] * w3 + sG[4 + i - 3] * w4 + sG[8 + i - 3] * w5;
     }
+    for (int i = 7; i < 13 + 2 * nj; ++i) {
+      float s = cj * Wc[(i - 1) * nw];
+      if (i == j) s += curv_speed;
+      Qc[i * n] = s;
+    }
+    for (int i = 13 + 2 * nj; i < g0; ++i) Qc[i * n] = cs.rc[i] * cj * Wc[(i - 1) * nw];
+    for (int i = g0; i < n; ++i) {
+      float s = cj * Wc[(i - 1 + nj) * nw];
+      if (cj_foot >= 0 && (i - g0) / 3 == cj_foot) s = fmaf(hcone * jf3[i - g0 - 3 * cj_foot], jfj, s);
+      Qc[i * n] = s;
+    }
+  }
+  // the four quaternion columns: Q[i][3+k] = sum_b (dr_i)' W[.][3..5] G[.][k]
+  for (int idx = tid; idx < 4 * n; idx += NT) {
+    const int i = idx >> 2, k = idx & 3;
+    const float g3 = sG[k], g4 = sG[4 + k], g5 = sG[8 + k];
+    const int ai = cs.ra[i];
+    float s;
+    if (ai >= 0) {
+      s = cs.rc[i] * (g3 * W[ai * nw + 3] + g4 * W[ai * nw + 4] + g5 * W[ai * nw + 5]);
+    } else {
+      s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        s = fmaf(sG[r * 4 + i - 3], g3 * W[(3 + r) * nw + 3] + g4 * W[(3 + r) * nw + 4] + g5 * W[(3 + r) * nw + 5], s);
+    }
+    Q[i * n + 3 + k] = s;
   }
   if (!term) {
     float* M = o.M + (size_t(e) * N + t) * n * m;
@@ -476,9 +488,10 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int N = io.N;
-  if (warp >= io.E * NALPHA) return;
-  const int e = warp / NALPHA, ia = warp - e * NALPHA;
+  if (warp >= io.E * o.nia) return;
+  const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
   if (io.done && io.done[e]) return;
+  if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
   const int n = md.n, m = md.m;
   const float alpha = exp2f(-float(ia));
   const float* W = io.W + size_t(e) * io.w_stride;
@@ -518,10 +531,7 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
     theta += __shfl_xor_sync(0xffffffffu, theta, s);
     phi += __shfl_xor_sync(0xffffffffu, phi, s);
   }
-  if (lane == 0) {
-    o.ls_theta[e * NALPHA + ia] = theta;
-    o.ls_phi[e * NALPHA + ia] = phi;
-  }
+  trial_finish(io, o, e, ia, lane, n, theta, phi);
 }
 
 template <int NV, int NC, int MAXD, int NT>
@@ -566,7 +576,7 @@ inline int wb_class_linearize(const WbModel& h, const WbModel* dev, const ModelI
 template <int NB, int NV, int NC>
 inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
   const int wpb = 2;
-  const int blocks = (io.E * NALPHA + wpb - 1) / wpb;
+  const int blocks = (io.E * to.nia + wpb - 1) / wpb;
   wb_trial_kernel<NB, NV, NC><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }

@@ -38,7 +38,8 @@ def _unwrap(p):
 class MpcSolver:
     """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
 
-    def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None):
+    def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None,
+                 eager_line_search=False):
         if not torch.cuda.is_available():
             raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
@@ -53,13 +54,18 @@ class MpcSolver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mpxb_model_create(C.byref(self.desc), C.byref(handle)), "mpxb_model_create")
         self.handle = handle
+        # lazy (default): alpha = 1 first, the ten smaller steps only where it is rejected -- same X, U, V, alpha_index;
+        # eager: all 11 trial points for every environment (fills the ls_theta / ls_phi views completely)
+        self.eager_line_search = bool(eager_line_search)
+        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_EAGER_LINE_SEARCH, int(self.eager_line_search)),
+                   "mpxb_model_set_option")
         self.ws_bytes = self.lib.mpxb_workspace_bytes(self.handle, self.n_env, self.lq_mode)
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         E = self.n_env
         self.alpha_index = torch.zeros(E, dtype=torch.int32, device=self.device)
         self.iters = torch.zeros(E, dtype=torch.int32, device=self.device)
         self.status = torch.zeros(E, dtype=torch.int32, device=self.device)
-        self.launches_per_call = 4 * self.max_iter
+        self.launches_per_call = (4 if self.eager_line_search else 5) * self.max_iter
 
     def __del__(self):
         try:
