@@ -784,22 +784,22 @@ struct WbTangentSink {
   }
 };
 
-// x <- (L L')^-1 x with the strictly-lower part of L in Lm (ld) and its diagonal in dL; K is the exact size so the
-// loops unroll and x stays in registers
-template <int K> HD void wb_tri_solve(const float* Lm, int ld, const float* dL, float* x) {
+// x <- (L L')^-1 x with the strictly-lower part of L in Lm (ld) and the RECIPROCAL of its diagonal in idL; K is the
+// exact size so the loops unroll and x stays in registers
+template <int K> HD void wb_tri_solve(const float* Lm, int ld, const float* idL, float* x) {
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     float s = x[i];
 #pragma unroll
     for (int p = 0; p < i; ++p) s = fmaf(-Lm[i * ld + p], x[p], s);
-    x[i] = s / dL[i];
+    x[i] = s * idL[i];
   }
 #pragma unroll
   for (int i = K - 1; i >= 0; --i) {
     float s = x[i];
 #pragma unroll
     for (int p = i + 1; p < K; ++p) s = fmaf(-Lm[p * ld + i], x[p], s);
-    x[i] = s / dL[i];
+    x[i] = s * idL[i];
   }
 }
 
@@ -808,7 +808,7 @@ template <int NV, int NC> struct WbKnot {
   static constexpr int NF = 3 * NC, NX = 13 + 2 * (NV - 6) + 2 * NF;
   float M[NV * NV];      // qM -> strictly-lower Cholesky factor in place (diagonal in dL)
   float J[NV * NF], MiJ[NV * NF], JMJ[NF * NF];
-  float dL[NV], dLc[NF], D[NV], tmd[NV], w[NV], a[NV], z[NV], wvz[NV];
+  float dL[NV], dLc[NF], D[NV]  /* dL, dLc: reciprocal Cholesky diagonals */, tmd[NV], w[NV], a[NV], z[NV], wvz[NV];
   float y[NF], grf[NF], feet[NF];
   float xn[NX], Gq[16], Gw[12];
 };
@@ -828,11 +828,11 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
   for (int j = 0; j < nv; ++j) {
     float sjj = k.M[j * NV + j];
     for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
-    const float dj = sqrtf(sjj);
+    const float dj = 1.f / sqrtf(sjj);
     for (int i = j + 1 + lane; i < nv; i += nl) {
       float s = k.M[i * NV + j];
       for (int p = 0; p < j; ++p) s = fmaf(-k.M[i * NV + p], k.M[j * NV + p], s);
-      k.M[i * NV + j] = s / dj;
+      k.M[i * NV + j] = s * dj;
     }
     if (lane == 0) k.dL[j] = dj;
     sync();
@@ -841,14 +841,18 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     for (int c = lane; c <= nf; c += nl) {
       if (c < nf) {
         float col[NV];
-        for (int i = 0; i < nv; ++i) col[i] = k.MiJ[i * NF + c];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) col[i] = k.MiJ[i * NF + c];
         wb_tri_solve<NV>(k.M, NV, k.dL, col);
-        for (int i = 0; i < nv; ++i) k.MiJ[i * NF + c] = col[i];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) k.MiJ[i * NF + c] = col[i];
       } else {
         float col[NV];
-        for (int i = 0; i < nv; ++i) col[i] = k.tmd[i];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) col[i] = k.tmd[i];
         wb_tri_solve<NV>(k.M, NV, k.dL, col);
-        for (int i = 0; i < nv; ++i) k.w[i] = col[i];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) k.w[i] = col[i];
       }
     }
     sync();
@@ -872,16 +876,23 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     for (int j = 0; j < nf; ++j) {
       float sjj = k.JMJ[j * NF + j];
       for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
-      const float dj = sqrtf(sjj);
+      const float dj = 1.f / sqrtf(sjj);
       for (int i = j + 1 + lane; i < nf; i += nl) {
         float s = k.JMJ[i * NF + j];
         for (int p = 0; p < j; ++p) s = fmaf(-k.JMJ[i * NF + p], k.JMJ[j * NF + p], s);
-        k.JMJ[i * NF + j] = s / dj;
+        k.JMJ[i * NF + j] = s * dj;
       }
       if (lane == 0) k.dLc[j] = dj;
       sync();
     }
-    if (lane == 0) { float yy[NF]; for (int c = 0; c < NF; ++c) yy[c] = k.y[c]; wb_tri_solve<NF>(k.JMJ, NF, k.dLc, yy); for (int c = 0; c < NF; ++c) k.y[c] = yy[c]; }
+    if (lane == 0) {
+      float yy[NF];
+#pragma unroll
+      for (int c = 0; c < NF; ++c) yy[c] = k.y[c];
+      wb_tri_solve<NF>(k.JMJ, NF, k.dLc, yy);
+#pragma unroll
+      for (int c = 0; c < NF; ++c) k.y[c] = yy[c];
+    }
     sync();
     for (int c = lane; c < nf; c += nl) k.grf[c] = k.y[c] * contact[c / 3];
     sync();
@@ -898,13 +909,15 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     sync();
     if (lane == 0) {
       float col[NV];
-      for (int i = 0; i < nv; ++i) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
         float s = k.tmd[i];
         for (int c = 0; c < nf; ++c) s = fmaf(k.J[i * NF + c], k.grf[c], s);
         col[i] = s;
       }
       wb_tri_solve<NV>(k.M, NV, k.dL, col);
-      for (int i = 0; i < nv; ++i) k.a[i] = col[i];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) k.a[i] = col[i];
     }
   }
   sync();

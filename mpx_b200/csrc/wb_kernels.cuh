@@ -389,6 +389,11 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 //   S6  (direction, body) force perturbations + subtree sums
 //   S7  thread d: folded tangents of direction d (analytic) -> column d of [A | B] (wb_s3_tangent), A'V / B'V
 //   P5  cost gradient, q, r, Gauss-Newton blocks
+// resident CTAs per SM the register allocation is tuned for (measured on B200, Go2 x1024: 6 CTAs of 64 threads at
+// 168 registers beat both 4 at 255 and 8 at 128)
+#ifndef MPXB_LIN3_MINB
+#define MPXB_LIN3_MINB (NT <= 64 ? 6 : (NT <= 96 ? 4 : 2))
+#endif
 template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
   WbKnot<NV, NC> k;
@@ -398,7 +403,7 @@ template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
 };
 
 template <int NB, int NV, int NC, int NI, int NT>
-__global__ void __launch_bounds__(NT) wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
+__global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
   using S = WbLin3Smem<NB, NV, NC, NI, NT>;
   constexpr int NDS = S::NDS, NQ = NV + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -46,6 +46,19 @@ for r, ch in zip(data, lines):
 ts = sum(v[0] for v in outer.values()) or 1
 ti = sum(v[1] for v in outer.values()) or 1
 print("total warp instructions", ti, "samples", ts)
+if os.environ.get("INNER"):
+    # INNER=<outer line>: break that stage down by the next frame of the inline chain
+    tgt = int(os.environ["INNER"])
+    inner = collections.defaultdict(lambda: [0, 0])
+    for r, ch in zip(data, lines):
+        if ch[-1][1] != tgt:
+            continue
+        k = ch[-2] if len(ch) > 1 else ch[-1]
+        inner[k][0] += int(r[ix["# Samples"]] or 0)
+        inner[k][1] += int(r[ix["Instructions Executed"]] or 0)
+    for k, v in sorted(inner.items(), key=lambda x: -x[1][0])[:top]:
+        print(f"  inner {k[0]}:{k[1]:<5d} samples {100 * v[0] / ts:5.1f}%  inst {100 * v[1] / ti:5.1f}%")
+    sys.exit(0)
 for k, v in sorted(outer.items(), key=lambda x: -x[1][0])[:top]:
     lanes = v[2] / v[1] if v[1] else 0
     print(f"{k[0]}:{k[1]:<5d} samples {100 * v[0] / ts:5.1f}%  inst {100 * v[1] / ti:5.1f}%  lanes/inst {lanes:4.1f}")
