@@ -17,6 +17,7 @@ struct LqArgs {
   // outputs: K[N,m,n] k[N,m] P[N+1,n,n] p[N+1,n] dX[N+1,n] dU[N,m] dV[N+1,n] slope[E]
   float *K, *k, *P, *p, *dX, *dU, *dV, *slope;
   const int32_t* done;  // per env: skip when != 0 (device-side SQP loop), may be null
+  int nzc;              // leading columns of A that can be non-zero (0 or >= n: all); columns >= nzc must hold zeros
 };
 
 constexpr int lq_pad(int n) { return (n + 3) & ~3; }
@@ -32,9 +33,11 @@ template <int n, int m> struct LqSmemLayout {
   static constexpr int oH = oPB + LN * LM;   // [LM][LN]
   static constexpr int oG = oH + LM * LN;    // [LM][LM]
   static constexpr int oK = oG + LM * LM;    // [LM][LN]
-  static constexpr int oVec = oK + LM * LN;  // p, w, c, q, h, kk, r : 4*LN + 3*LM
-  static constexpr int total = oVec + 4 * LN + 3 * LM + 8;
+  static constexpr int oVec = oK + LM * LN;  // p, w, c, q, h, kk, r, 1/diag(chol G) : 4*LN + 4*LM
+  static constexpr int total = oVec + 4 * LN + 4 * LM + 8;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
+  // resident CTAs per SM that shared memory allows (227 KB usable, 1 KB reserved per CTA), capped at 4
+  static constexpr int min_blocks = (232448 / (bytes + 1024)) < 1 ? 1 : ((232448 / (bytes + 1024)) > 4 ? 4 : int(232448 / (bytes + 1024)));
 };
 
 // C[MT*4, NT*4] = op(A) * op(B); op(A)(i,k) = TA ? A[k*lda+i] : A[i*lda+k]; op(B)(k,j) = TB ? B[j*ldb+k] : B[k*ldb+j].
@@ -153,30 +156,85 @@ __device__ __forceinline__ void lq_rollout_dual(const LqArgs& a, int e, int tid,
   }
 }
 
+// acc[4][4] += A[0:K, i0:i0+4]^T B[0:K, j0:j0+4]  (both operands k-major in shared memory, one LDS.128 each per k)
+__device__ __forceinline__ void tile_atb(float (&acc)[4][4], const float* __restrict__ A, int lda, int i0,
+                                         const float* __restrict__ B, int ldb, int j0, int K) {
+#pragma unroll 4
+  for (int kk = 0; kk < K; ++kk) {
+    const float4 ta = *reinterpret_cast<const float4*>(A + kk * lda + i0);
+    const float4 tb = *reinterpret_cast<const float4*>(B + kk * ldb + j0);
+    const float av[4] = {ta.x, ta.y, ta.z, ta.w}, bv[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
+  }
+}
+__device__ __forceinline__ void tile_zero(float (&acc)[4][4]) {
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+}
+__device__ __forceinline__ void tile_store(float* __restrict__ C, int ldc, int i0, int j0, const float (&acc)[4][4]) {
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+    *reinterpret_cast<float4*>(C + (i0 + x) * ldc + j0) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// asynchronous copy of the leading `cols` columns of a [rows, gcols] global matrix into a [., ld] shared tile
+__device__ __forceinline__ void cp_async_matrix(float* dst, int ld, const float* src, int rows, int gcols, int cols, int tid,
+                                                int nthreads) {
+  for (int idx = tid; idx < rows * cols; idx += nthreads) {
+    const int i = idx / cols, j = idx - i * cols;
+    cp_async4(dst + i * ld + j, src + i * gcols + j);
+  }
+}
+
+// Sequential Riccati backward pass + rollout, one CTA per environment.
+//
+// Per knot (lqr_step, primal_tvlqr.py:11-52), with Az = the leading nzc columns of A_t (columns >= nzc are zero:
+// the foot / GRF tail of the whole-body state never enters the dynamics; nzc = n for a generic problem):
+//   S1  T1 = P Az, PB = P B, w = p + P c                      (P is bitwise symmetric -> P^T form, LDS.128 operands)
+//   S2  X = Az^T T1 (nzc x nzc block), H = B^T T1, G = B^T PB, h = B^T w + r, q' = q + A^T w
+//       -> A_{t-1}, B_{t-1} and Q_t are prefetched with cp.async while S3..S6 run
+//   S3  H += M^T, G = sym(R + G)      S4  Cholesky of G      S5  [K k] = -G^-1 [H h]
+//   S6  XY = X + K^T H, p = q' + K^T h
+//   S7  P = sym(Q + XY)   (pair-owned, conflict-free skewed walk; the reference's inner sym(A^T P A) only reorders
+//       roundings of the same symmetric sum)
 template <int n, int m, int NT>
-__global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
+__global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_kernel(LqArgs a) {
   using L = LqSmemLayout<n, m>;
-  constexpr int LN = L::LN, LM = L::LM;
+  constexpr int LN = L::LN, LM = L::LM, TN = LN / 4, TM = LM / 4;
   extern __shared__ __align__(16) float smem[];
-  float* sP = smem + L::oP;
-  float* sA = smem + L::oA;
-  float* sT = smem + L::oT;
-  float* sB = smem + L::oB;
-  float* sPB = smem + L::oPB;
-  float* sH = smem + L::oH;
-  float* sG = smem + L::oG;
-  float* sK = smem + L::oK;
+  float* sP = smem + L::oP;    // P_{t+1}; X / XY of the step; P_t
+  float* sA = smem + L::oA;    // A_t (leading LZ columns)
+  float* sT = smem + L::oT;    // T1 = P A; then Q_t
+  float* sB = smem + L::oB;    // [LN][LM]
+  float* sPB = smem + L::oPB;  // [LN][LM]
+  float* sH = smem + L::oH;    // [LM][LN]
+  float* sG = smem + L::oG;    // [LM][LM]
+  float* sK = smem + L::oK;    // [LM][LN]
   float* sp = smem + L::oVec;  // p   [LN]
   float* sw = sp + LN;         // w = p + P c
-  float* sc = sw + LN;         // c_t
-  float* sq = sc + LN;         // scratch n-vector
+  float* sc = sw + LN;         // c_{t+1}
+  float* sq = sc + LN;         // q_t + A^T w
   float* sh = sq + LN;         // h [LM]
   float* skk = sh + LM;        // k [LM]
   float* sr = skk + LM;        // r_t [LM]
+  float* sgi = sr + LM;        // reciprocal Cholesky diagonal of G [LM] (inside the + 8 ... see layout)
   const int e = blockIdx.x;
   const int tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
+  const int nzc = (a.nzc > 0 && a.nzc < n) ? a.nzc : n;
+  const int LZ = (nzc + 3) & ~3, TZ = LZ / 4;
+  const int acols = (LZ < n) ? LZ : n;  // columns of A fetched (those in [nzc, LZ) are stored zeros)
   const float* gA = a.A + size_t(e) * N * n * n;
   const float* gB = a.B + size_t(e) * N * n * m;
   const float* gQ = a.Q + size_t(e) * (N + 1) * n * n;
@@ -190,49 +248,94 @@ __global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
   float* gP = a.P + size_t(e) * (N + 1) * n * n;
   float* gp = a.p + size_t(e) * (N + 1) * n;
 
-  // terminal value function: P_N = Q_N, p_N = q_N   (primal_tvlqr.py:136)
-  load_padded(sP, LN, LN, gQ + size_t(N) * n * n, n, n, tid, NT);
-  for (int i = tid; i < LN; i += NT) sp[i] = (i < n) ? gq[size_t(N) * n + i] : 0.f;
-  for (int idx = tid; idx < n * n; idx += NT) gP[size_t(N) * n * n + idx] = gQ[size_t(N) * n * n + idx];
-  for (int i = tid; i < n; i += NT) gp[size_t(N) * n + i] = gq[size_t(N) * n + i];
+  // zero every buffer once: the padding of the cp.async targets is never written again
+  for (int i = tid; i < L::total; i += NT) smem[i] = 0.f;
   __syncthreads();
+  // terminal value function: P_N = Q_N, p_N = q_N   (primal_tvlqr.py:136); first A, B
+  // (stored transposed: the products below read P^T, and Q_N is the one P that need not be symmetric)
+  for (int idx = tid; idx < n * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    cp_async4(sP + j * LN + i, gQ + size_t(N) * n * n + idx);
+  }
+  cp_async_matrix(sA, LN, gA + size_t(N - 1) * n * n, n, n, acols, tid, NT);
+  cp_async_matrix(sB, LM, gB + size_t(N - 1) * n * m, n, m, m, tid, NT);
+  cp_async_commit();
+  for (int i = tid; i < n; i += NT) { const float v = gq[size_t(N) * n + i]; sp[i] = v; gp[size_t(N) * n + i] = v; }
+  for (int idx = tid; idx < n * n; idx += NT) gP[size_t(N) * n * n + idx] = gQ[size_t(N) * n * n + idx];
 
   for (int t = N - 1; t >= 0; --t) {
-    load_padded(sA, LN, LN, gA + size_t(t) * n * n, n, n, tid, NT);
-    load_padded(sB, LM, LN, gB + size_t(t) * n * m, n, m, tid, NT);
-    for (int i = tid; i < LN; i += NT) sc[i] = (i < n) ? gc[size_t(t + 1) * n + i] : 0.f;
-    for (int i = tid; i < LM; i += NT) sr[i] = (i < m) ? gr[size_t(t) * m + i] : 0.f;
+    for (int i = tid; i < n; i += NT) sc[i] = gc[size_t(t + 1) * n + i];
+    for (int i = tid; i < m; i += NT) sr[i] = gr[size_t(t) * m + i];
+    cp_async_wait_all();
     __syncthreads();
-    // w = p + P c
-    for (int i = tid; i < LN; i += NT) {
-      float s = sp[i];
-      for (int j = 0; j < n; ++j) s = fmaf(sP[i * LN + j], sc[j], s);
-      sw[i] = s;
-    }
-    // T1 = P A,  PB = P B
-    gemm_tiles<false, false>(sT, LN, sP, LN, sA, LN, LN / 4, LN / 4, n, tid, NT);
-    gemm_tiles<false, false>(sPB, LM, sP, LN, sB, LM, LN / 4, LM / 4, n, tid, NT);
-    __syncthreads();
-    // X = A^T T1 -> sP (old P is dead);  H = B^T T1 ;  G = B^T PB ;  h = B^T w + r
-    gemm_tiles<true, false>(sP, LN, sA, LN, sT, LN, LN / 4, LN / 4, n, tid, NT);
-    gemm_tiles<true, false>(sH, LN, sB, LM, sT, LN, LM / 4, LN / 4, n, tid, NT);
-    gemm_tiles<true, false>(sG, LM, sB, LM, sPB, LM, LM / 4, LM / 4, n, tid, NT);
-    for (int i = tid; i < LM; i += NT) {
-      float s = sr[i];
-      for (int j = 0; j < n; ++j) s = fmaf(sB[j * LM + i], sw[j], s);
-      sh[i] = s;
-    }
-    // q-scratch = q_t + A^T w
-    for (int i = tid; i < LN; i += NT) {
-      float s = (i < n) ? gq[size_t(t) * n + i] : 0.f;
-      for (int j = 0; j < n; ++j) s = fmaf(sA[j * LN + i], sw[j], s);
-      sq[i] = s;
+    // ---- S1
+    for (int tile = tid; tile < TN * TZ + TN * TM + LN; tile += NT) {
+      float acc[4][4];
+      if (tile < TN * TZ) {
+        const int i0 = (tile / TZ) * 4, j0 = (tile % TZ) * 4;
+        tile_zero(acc);
+        tile_atb(acc, sP, LN, i0, sA, LN, j0, n);
+        tile_store(sT, LN, i0, j0, acc);
+      } else if (tile < TN * TZ + TN * TM) {
+        const int tt = tile - TN * TZ;
+        const int i0 = (tt / TM) * 4, j0 = (tt % TM) * 4;
+        tile_zero(acc);
+        tile_atb(acc, sP, LN, i0, sB, LM, j0, n);
+        tile_store(sPB, LM, i0, j0, acc);
+      } else {
+        const int i = tile - TN * TZ - TN * TM;
+        float s = sp[i];
+        for (int j = 0; j < n; ++j) s = fmaf(sP[j * LN + i], sc[j], s);
+        sw[i] = (i < n) ? s : 0.f;
+      }
     }
     __syncthreads();
-    // H += M^T ; G = sym(R + G)
+    // ---- S2
+    for (int tile = tid; tile < TZ * TZ + TM * TZ + TM * TM + LM + LN; tile += NT) {
+      float acc[4][4];
+      if (tile < TZ * TZ) {
+        const int i0 = (tile / TZ) * 4, j0 = (tile % TZ) * 4;
+        tile_zero(acc);
+        tile_atb(acc, sA, LN, i0, sT, LN, j0, n);
+        tile_store(sP, LN, i0, j0, acc);  // P_{t+1} is dead
+      } else if (tile < TZ * TZ + TM * TZ) {
+        const int tt = tile - TZ * TZ;
+        const int i0 = (tt / TZ) * 4, j0 = (tt % TZ) * 4;
+        tile_zero(acc);
+        tile_atb(acc, sB, LM, i0, sT, LN, j0, n);
+        tile_store(sH, LN, i0, j0, acc);
+      } else if (tile < TZ * TZ + TM * TZ + TM * TM) {
+        const int tt = tile - TZ * TZ - TM * TZ;
+        const int i0 = (tt / TM) * 4, j0 = (tt % TM) * 4;
+        tile_zero(acc);
+        tile_atb(acc, sB, LM, i0, sPB, LM, j0, n);
+        tile_store(sG, LM, i0, j0, acc);
+      } else if (tile < TZ * TZ + TM * TZ + TM * TM + LM) {
+        const int i = tile - TZ * TZ - TM * TZ - TM * TM;
+        float s = sr[i];
+        for (int j = 0; j < n; ++j) s = fmaf(sB[j * LM + i], sw[j], s);
+        sh[i] = (i < m) ? s : 0.f;
+      } else {
+        const int i = tile - TZ * TZ - TM * TZ - TM * TM - LM;
+        float s = (i < n) ? gq[size_t(t) * n + i] : 0.f;
+        if (i < LZ)
+          for (int j = 0; j < n; ++j) s = fmaf(sA[j * LN + i], sw[j], s);
+        sq[i] = s;
+      }
+    }
+    __syncthreads();
+    // prefetch: Q_t over T1, A_{t-1} / B_{t-1} over A_t / B_t
+    cp_async_matrix(sT, LN, gQ + size_t(t) * n * n, n, n, n, tid, NT);
+    if (t > 0) {
+      cp_async_matrix(sA, LN, gA + size_t(t - 1) * n * n, n, n, acols, tid, NT);
+      cp_async_matrix(sB, LM, gB + size_t(t - 1) * n * m, n, m, m, tid, NT);
+    }
+    cp_async_commit();
+    // ---- S3: H (columns >= LZ hold no B^T P A part) += M^T ; G = sym(R + G)
     for (int idx = tid; idx < m * n; idx += NT) {
-      const int i = idx / n, j = idx - i * n;
-      sH[i * LN + j] += gM[size_t(t) * n * m + j * m + i];
+      const int j = idx / m, i = idx - j * m;  // M is [n][m]: coalesced read
+      const float mv = gM[size_t(t) * n * m + idx];
+      sH[i * LN + j] = (j < LZ ? sH[i * LN + j] : 0.f) + mv;
     }
     for (int idx = tid; idx < m * m; idx += NT) {
       const int i = idx / m, j = idx - i * m;
@@ -240,21 +343,19 @@ __global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
         const float gij = gR[size_t(t) * m * m + i * m + j] + sG[i * LM + j];
         const float gji = gR[size_t(t) * m * m + j * m + i] + sG[j * LM + i];
         const float s = 0.5f * (gij + gji);
-        // both halves are read only by this thread before being written
-        sG[i * LM + j] = s;
+        sG[i * LM + j] = s;  // both halves are read only by this thread before being written
         sG[j * LM + i] = s;
       }
     }
     __syncthreads();
-    // Cholesky G = L L^T in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
+    // ---- S4: Cholesky G = L L^T in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
     if (tid < 32) {
       for (int j = 0; j < m; ++j) {
         float d = sG[j * LM + j];
         for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LM + k2], sG[j * LM + k2], d);
-        d = sqrtf(d);
-        const float inv = 1.f / d;
+        const float inv = 1.f / sqrtf(d);
         __syncwarp();
-        if (tid == 0) sG[j * LM + j] = d;
+        if (tid == 0) sgi[j] = inv;
         for (int i = j + 1 + tid; i < m; i += 32) {
           float s = sG[i * LM + j];
           for (int k2 = 0; k2 < j; ++k2) s = fmaf(-sG[i * LM + k2], sG[j * LM + k2], s);
@@ -264,64 +365,78 @@ __global__ void __launch_bounds__(NT) lq_seq_kernel(LqArgs a) {
       }
     }
     __syncthreads();
-    // [K k] = -G^-1 [H h]: one thread per right-hand-side column
+    // ---- S5: [K k] = -G^-1 [H h]: one thread per right-hand-side column
     for (int col = tid; col <= n; col += NT) {
       float y[m];
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < m; ++i) {
         float s = -((col < n) ? sH[i * LN + col] : sh[i]);
+#pragma unroll
         for (int k2 = 0; k2 < i; ++k2) s = fmaf(-sG[i * LM + k2], y[k2], s);
-        y[i] = s / sG[i * LM + i];
+        y[i] = s * sgi[i];
       }
-#pragma unroll 1
+#pragma unroll
       for (int i = m - 1; i >= 0; --i) {
         float s = y[i];
+#pragma unroll
         for (int k2 = i + 1; k2 < m; ++k2) s = fmaf(-sG[k2 * LM + i], y[k2], s);
-        y[i] = s / sG[i * LM + i];
+        y[i] = s * sgi[i];
       }
       if (col < n) {
-        for (int i = 0; i < m; ++i) sK[i * LN + col] = y[i];
+#pragma unroll
+        for (int i = 0; i < m; ++i) { sK[i * LN + col] = y[i]; gK[size_t(t) * m * n + i * n + col] = y[i]; }
       } else {
-        for (int i = 0; i < m; ++i) skk[i] = y[i];
+#pragma unroll
+        for (int i = 0; i < m; ++i) { skk[i] = y[i]; gk[size_t(t) * m + i] = y[i]; }
       }
     }
-    // zero the padding of K (rows m..LM-1 and cols n..LN-1) once per step so K^T H tiles stay clean
-    for (int idx = tid; idx < LM * LN; idx += NT) {
-      const int i = idx / LN, j = idx - i * LN;
-      if (i >= m || j >= n) sK[idx] = 0.f;
-    }
     __syncthreads();
-    // Y = K^T H -> sA (A is dead); then Y += Q + sym(X)
-    gemm_tiles<true, false>(sA, LN, sK, LN, sH, LN, LN / 4, LN / 4, m, tid, NT);
-    // p_new = q + A^T w + K^T h
-    for (int i = tid; i < LN; i += NT) {
-      float s = sq[i];
-      for (int j = 0; j < m; ++j) s = fmaf(sK[j * LN + i], sh[j], s);
-      sp[i] = (i < n) ? s : 0.f;
+    // ---- S6: XY = X + K^T H (X lives in the leading LZ x LZ block of sP), p = q' + K^T h
+    for (int tile = tid; tile < TN * TN + LN; tile += NT) {
+      if (tile < TN * TN) {
+        const int ti = tile / TN, tj = tile % TN;
+        const int i0 = ti * 4, j0 = tj * 4;
+        float acc[4][4];
+        if (ti < TZ && tj < TZ) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float4 v = *reinterpret_cast<const float4*>(sP + (i0 + x) * LN + j0);
+            acc[x][0] = v.x; acc[x][1] = v.y; acc[x][2] = v.z; acc[x][3] = v.w;
+          }
+        } else {
+          tile_zero(acc);
+        }
+        tile_atb(acc, sK, LN, i0, sH, LN, j0, m);
+        tile_store(sP, LN, i0, j0, acc);
+      } else {
+        const int i = tile - TN * TN;
+        float s = sq[i];
+        for (int j = 0; j < m; ++j) s = fmaf(sK[j * LN + i], sh[j], s);
+        s = (i < n) ? s : 0.f;
+        sp[i] = s;
+        if (i < n) gp[size_t(t) * n + i] = s;
+      }
     }
+    cp_async_wait_all();
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += NT) {
-      const int i = idx / n, j = idx - i * n;
-      sA[i * LN + j] += gQ[size_t(t) * n * n + idx] + 0.5f * (sP[i * LN + j] + sP[j * LN + i]);
+    // ---- S7: P = sym(Q + XY): unordered pairs {i, (i + d) mod LN}; lanes walk i, so both accesses hit 32 banks
+    for (int idx = tid; idx < (LN / 2 + 1) * LN; idx += NT) {
+      const int d = idx / LN, i = idx - d * LN;
+      int j = i + d;
+      if (j >= LN) j -= LN;
+      if ((2 * d == LN && i >= LN / 2) || i >= n || j >= n) continue;
+      const float zij = sT[i * LN + j] + sP[i * LN + j];
+      const float zji = sT[j * LN + i] + sP[j * LN + i];
+      const float s = 0.5f * (zij + zji);
+      sP[i * LN + j] = s;
+      sP[j * LN + i] = s;
     }
-    __syncthreads();
-    // P = sym(Y)
-    for (int idx = tid; idx < LN * LN; idx += NT) {
-      const int i = idx / LN, j = idx - i * LN;
-      sP[idx] = (i < n && j < n) ? 0.5f * (sA[i * LN + j] + sA[j * LN + i]) : 0.f;
-    }
-    // store gains
-    for (int idx = tid; idx < m * n; idx += NT) {
-      const int i = idx / n, j = idx - i * n;
-      gK[size_t(t) * m * n + idx] = sK[i * LN + j];
-    }
-    for (int i = tid; i < m; i += NT) gk[size_t(t) * m + i] = skk[i];
-    for (int i = tid; i < n; i += NT) gp[size_t(t) * n + i] = sp[i];
     __syncthreads();
     for (int idx = tid; idx < n * n; idx += NT) {
       const int i = idx / n, j = idx - i * n;
       gP[size_t(t) * n * n + idx] = sP[i * LN + j];
     }
+    // the next S1 reads sP (after its barrier); sT (Q) is dead, T1 overwrites it after that barrier as well
   }
   __syncthreads();
 

@@ -193,7 +193,9 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     if (pev) cudaEventRecord(pev[1], st);
     // K2
     LqArgs la{E, N, ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c,
-              ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done};
+              ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done,
+              // whole-body models: the foot / GRF tail of the state never enters f, so those columns of A are zero
+              d.kind == MPXB_KIND_SRBD ? 0 : 13 + 2 * d.n_joints};
     int rc = (lq_mode == MPXB_LQ_SEQUENTIAL) ? dispatch_lq_seq(n, m, la, st)
                                              : dispatch_lq_scan(n, m, la, ws + L.scan, st);
     if (rc != MPXB_OK) return rc;
@@ -341,7 +343,7 @@ int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const floa
                const float* r, const float* M, const float* A, const float* B, const float* c /*[E,N+1,n]: c[0]=x0 offset*/,
                float* K, float* k, float* P, float* p, float* dX, float* dU, float* dV, float* slope, void* scan_ws) {
   if (!Q || !q || !R || !r || !M || !A || !B || !c || !K || !k || !P || !p || !dX || !dU || !dV || !slope) return MPXB_EINVAL;
-  LqArgs la{E, N, A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, slope, nullptr};
+  LqArgs la{E, N, A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, slope, nullptr, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lq_mode == MPXB_LQ_SEQUENTIAL) return dispatch_lq_seq(n, m, la, st);
   if (!scan_ws) return MPXB_EINVAL;
