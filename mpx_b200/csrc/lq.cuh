@@ -20,7 +20,7 @@ struct LqArgs {
   int nzc;              // leading columns of A that can be non-zero (0 or >= n: all); columns >= nzc must hold zeros
 };
 
-constexpr int lq_pad(int n) { return (n + 3) & ~3; }
+__host__ __device__ constexpr int lq_pad(int n) { return (n + 3) & ~3; }
 
 template <int n, int m> struct LqSmemLayout {
   static constexpr int LN = lq_pad(n), LM = lq_pad(m);
@@ -87,6 +87,167 @@ __device__ __forceinline__ void load_padded(float* __restrict__ dst, int ld, int
   for (int idx = tid; idx < prow * ld; idx += nthreads) {
     const int i = idx / ld, j = idx - i * ld;
     dst[idx] = (i < rows && j < cols) ? src[i * cols + j] : 0.f;
+  }
+}
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// asynchronous copy of the leading `cols` columns of a [rows, gcols] global matrix into a [., ld] shared tile
+__device__ __forceinline__ void cp_async_matrix(float* dst, int ld, const float* src, int rows, int gcols, int cols, int tid,
+                                                int nthreads) {
+  for (int idx = tid; idx < rows * cols; idx += nthreads) {
+    const int i = idx / cols, j = idx - i * cols;
+    cp_async4(dst + i * ld + j, src + i * gcols + j);
+  }
+}
+
+__host__ __device__ constexpr int lq_parts(int rows, int nthreads) {  // lanes that share one row: largest power of two with rows * p <= nthreads
+  int p = 32;
+  while (p > 1 && rows * p > nthreads) p >>= 1;
+  return p;
+}
+
+// Forward rollout + dual update + slope for the sequential backward pass (primal_tvlqr.py:478-498: dx_0 = c_0,
+// du_t = K_t dx_t + k_t, dx_{t+1} = A_t dx_t + B_t du_t + c_{t+1}; dual_tvlqr.py:19: dV_t = P_t dx_t + p_t).
+// The only serial chain is dx; its per-knot operands (K, A, B, q, r, c, k) are streamed through a cp.async double
+// buffer so a knot costs two shared-memory mat-vecs and three barriers.  dV needs no chain: it is evaluated for all
+// knots at once afterwards, one warp per row of P.  `smem` is the whole (now dead) backward-pass arena.
+template <int n, int m, int NT>
+__device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int tid, float* smem, int acols) {
+  constexpr int LN = lq_pad(n), LM = lq_pad(m);
+  constexpr int PD = lq_parts(m, NT), PX = lq_parts(n, NT);
+  constexpr int SB = 2 * m * n + n * LN + 2 * n + 2 * m;  // one stage: K | A | B | q | r | c | k
+  const int N = a.N;
+  const float* gA = a.A + size_t(e) * N * n * n;
+  const float* gB = a.B + size_t(e) * N * n * m;
+  const float* gq = a.q + size_t(e) * (N + 1) * n;
+  const float* gr = a.r + size_t(e) * N * m;
+  const float* gc = a.c + size_t(e) * (N + 1) * n;
+  const float* gK = a.K + size_t(e) * N * m * n;
+  const float* gk = a.k + size_t(e) * N * m;
+  const float* gP = a.P + size_t(e) * (N + 1) * n * n;
+  const float* gp = a.p + size_t(e) * (N + 1) * n;
+  float* gdX = a.dX + size_t(e) * (N + 1) * n;
+  float* gdU = a.dU + size_t(e) * N * m;
+  float* gdV = a.dV + size_t(e) * (N + 1) * n;
+  float* stage = smem;
+  float* sdx = smem + 2 * SB;  // [2][LN]
+  float* sdu = sdx + 2 * LN;   // [LM]
+  float* sred = sdu + LM;      // [NT / 32]
+  auto prefetch = [&](int t, int buf) {
+    float* st = stage + buf * SB;
+    float* sK = st;
+    float* sA = sK + m * n;
+    float* sB = sA + n * LN;
+    float* sq = sB + n * m;
+    float* sr = sq + n;
+    float* sc = sr + m;
+    float* sk = sc + n;
+    for (int i = tid; i < m * n; i += NT) cp_async4(sK + i, gK + size_t(t) * m * n + i);
+    cp_async_matrix(sA, acols, gA + size_t(t) * n * n, n, n, acols, tid, NT);
+    for (int i = tid; i < n * m; i += NT) cp_async4(sB + i, gB + size_t(t) * n * m + i);
+    for (int i = tid; i < n; i += NT) { cp_async4(sq + i, gq + size_t(t) * n + i); cp_async4(sc + i, gc + size_t(t + 1) * n + i); }
+    for (int i = tid; i < m; i += NT) { cp_async4(sr + i, gr + size_t(t) * m + i); cp_async4(sk + i, gk + size_t(t) * m + i); }
+    cp_async_commit();
+  };
+  __syncthreads();  // the backward pass is done with the arena
+  prefetch(0, 0);
+  for (int i = tid; i < n; i += NT) sdx[i] = gc[i];
+  float slope_acc = 0.f;
+  for (int t = 0; t < N; ++t) {
+    const float* st = stage + (t & 1) * SB;
+    const float* sK = st;
+    const float* sA = sK + m * n;
+    const float* sB = sA + n * LN;
+    const float* sq = sB + n * m;
+    const float* sr = sq + n;
+    const float* sc = sr + m;
+    const float* sk = sc + n;
+    const float* dx = sdx + (t & 1) * LN;
+    float* dxn = sdx + ((t + 1) & 1) * LN;
+    if (t + 1 < N) {
+      prefetch(t + 1, (t + 1) & 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    {  // du = K dx + k : PD lanes per row
+      const int row = tid / PD, part = tid - row * PD;
+      float s = 0.f;
+      if (row < m)
+        for (int j = part; j < n; j += PD) s = fmaf(sK[row * n + j], dx[j], s);
+#pragma unroll
+      for (int o = PD / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (row < m && part == 0) {
+        s += sk[row];
+        sdu[row] = s;
+        gdU[size_t(t) * m + row] = s;
+        slope_acc = fmaf(sr[row], s, slope_acc);
+      }
+    }
+    if (tid < n) {
+      gdX[size_t(t) * n + tid] = dx[tid];
+      slope_acc = fmaf(sq[tid], dx[tid], slope_acc);
+    }
+    __syncthreads();
+    {  // dx+ = A dx + B du + c : PX lanes per row
+      const int row = tid / PX, part = tid - row * PX;
+      float s = 0.f;
+      if (row < n) {
+        for (int j = part; j < acols; j += PX) s = fmaf(sA[row * acols + j], dx[j], s);
+        for (int j = part; j < m; j += PX) s = fmaf(sB[row * m + j], sdu[j], s);
+      }
+#pragma unroll
+      for (int o = PX / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (row < n && part == 0) dxn[row] = s + sc[row];
+    }
+    __syncthreads();
+  }
+  {
+    const float* dx = sdx + (N & 1) * LN;
+    if (tid < n) {
+      gdX[size_t(N) * n + tid] = dx[tid];
+      slope_acc = fmaf(gq[size_t(N) * n + tid], dx[tid], slope_acc);
+    }
+  }
+  // slope = sum q.dX + sum r.dU : fixed-order block reduction (deterministic)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) slope_acc += __shfl_xor_sync(0xffffffffu, slope_acc, o);
+  if ((tid & 31) == 0) sred[tid >> 5] = slope_acc;
+  __syncthreads();  // also publishes gdX to the whole block
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < NT / 32; ++w) s += sred[w];
+    a.slope[e] = s;
+  }
+  // dV_t = P_t dx_t + p_t for every knot: one warp per row, four rows in flight
+  const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
+  const int rows = (N + 1) * n;
+  for (int base = warp * 4; base < rows; base += nwarp * 4) {
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = base + u;
+      s[u] = 0.f;
+      if (r < rows) {
+        const int t = r / n;
+        const float* prow = gP + size_t(r) * n;
+        const float* dx = gdX + size_t(t) * n;
+        for (int j = lane; j < n; j += 32) s[u] = fmaf(prow[j], dx[j], s[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+      const int r = base + u;
+      if (lane == 0 && r < rows) gdV[r] = s[u] + gp[r];
+    }
   }
 }
 
@@ -181,21 +342,6 @@ __device__ __forceinline__ void tile_store(float* __restrict__ C, int ldc, int i
   for (int x = 0; x < 4; ++x)
     *reinterpret_cast<float4*>(C + (i0 + x) * ldc + j0) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
 }
-__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-// asynchronous copy of the leading `cols` columns of a [rows, gcols] global matrix into a [., ld] shared tile
-__device__ __forceinline__ void cp_async_matrix(float* dst, int ld, const float* src, int rows, int gcols, int cols, int tid,
-                                                int nthreads) {
-  for (int idx = tid; idx < rows * cols; idx += nthreads) {
-    const int i = idx / cols, j = idx - i * cols;
-    cp_async4(dst + i * ld + j, src + i * gcols + j);
-  }
-}
-
 // Sequential Riccati backward pass + rollout, one CTA per environment.
 //
 // Per knot (lqr_step, primal_tvlqr.py:11-52), with Az = the leading nzc columns of A_t (columns >= nzc are zero:
@@ -441,7 +587,7 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   __syncthreads();
 
   // ---- forward rollout + dual (primal_tvlqr.py:484-498, dual_tvlqr.py:19) ----
-  lq_rollout_dual<n, m, NT>(a, e, tid, sw, sq, sh);
+  lq_rollout_stream<n, m, NT>(a, e, tid, smem, acols);
 }
 
 }  // namespace mpxb
