@@ -120,7 +120,11 @@ template <int n, int m, int NT>
 __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int tid, float* smem, int acols) {
   constexpr int LN = lq_pad(n), LM = lq_pad(m);
   constexpr int PD = lq_parts(m, NT), PX = lq_parts(n, NT);
-  constexpr int SB = 2 * m * n + n * LN + 2 * n + 2 * m;  // one stage: K | A | B | q | r | c | k
+  // one stage: K | A (acols wide) | B | q | r | c | k | [P | p when two stages with P still fit the arena]
+  constexpr int ARENA = LqSmemLayout<n, m>::total;
+  const int SB0 = 2 * m * n + n * acols + 2 * n + 2 * m;
+  const bool withP = 2 * (SB0 + n * n + n) + 2 * LN + LM + NT / 32 <= ARENA;
+  const int SB = SB0 + (withP ? n * n + n : 0);
   const int N = a.N;
   const float* gA = a.A + size_t(e) * N * n * n;
   const float* gB = a.B + size_t(e) * N * n * m;
@@ -142,11 +146,16 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     float* st = stage + buf * SB;
     float* sK = st;
     float* sA = sK + m * n;
-    float* sB = sA + n * LN;
+    float* sB = sA + n * acols;
     float* sq = sB + n * m;
     float* sr = sq + n;
     float* sc = sr + m;
     float* sk = sc + n;
+    float* sPm = sk + m;
+    if (withP) {
+      for (int i = tid; i < n * n; i += NT) cp_async4(sPm + i, gP + size_t(t) * n * n + i);
+      for (int i = tid; i < n; i += NT) cp_async4(sPm + n * n + i, gp + size_t(t) * n + i);
+    }
     for (int i = tid; i < m * n; i += NT) cp_async4(sK + i, gK + size_t(t) * m * n + i);
     cp_async_matrix(sA, acols, gA + size_t(t) * n * n, n, n, acols, tid, NT);
     for (int i = tid; i < n * m; i += NT) cp_async4(sB + i, gB + size_t(t) * n * m + i);
@@ -162,11 +171,12 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     const float* st = stage + (t & 1) * SB;
     const float* sK = st;
     const float* sA = sK + m * n;
-    const float* sB = sA + n * LN;
+    const float* sB = sA + n * acols;
     const float* sq = sB + n * m;
     const float* sr = sq + n;
     const float* sc = sr + m;
     const float* sk = sc + n;
+    const float* sPm = sk + m;
     const float* dx = sdx + (t & 1) * LN;
     float* dxn = sdx + ((t + 1) & 1) * LN;
     if (t + 1 < N) {
@@ -193,6 +203,15 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     if (tid < n) {
       gdX[size_t(t) * n + tid] = dx[tid];
       slope_acc = fmaf(sq[tid], dx[tid], slope_acc);
+    }
+    if (withP) {  // dV_t = P_t dx_t + p_t, off the dx chain
+      const int row = tid / PX, part = tid - row * PX;
+      float s = 0.f;
+      if (row < n)
+        for (int j = part; j < n; j += PX) s = fmaf(sPm[row * n + j], dx[j], s);
+#pragma unroll
+      for (int o = PX / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (row < n && part == 0) gdV[size_t(t) * n + row] = s + sPm[n * n + row];
     }
     __syncthreads();
     {  // dx+ = A dx + B du + c : PX lanes per row
@@ -225,10 +244,11 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     for (int w = 0; w < NT / 32; ++w) s += sred[w];
     a.slope[e] = s;
   }
-  // dV_t = P_t dx_t + p_t for every knot: one warp per row, four rows in flight
+  // dV_t = P_t dx_t + p_t for the knots not covered above (all of them when P did not fit the stages): one warp per
+  // row, four rows in flight
   const int warp = tid >> 5, lane = tid & 31, nwarp = NT >> 5;
   const int rows = (N + 1) * n;
-  for (int base = warp * 4; base < rows; base += nwarp * 4) {
+  for (int base = (withP ? N * n : 0) + warp * 4; base < rows; base += nwarp * 4) {
     float s[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
