@@ -955,9 +955,16 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
 // out(i, value), i = 0..n-1 in increasing order.
 //   is_u == 0: state direction `dir` in [0, 7+nj+nv) ; is_u == 1: control direction `dir` in [0, m).
 // t1, t2, e, h, dfeet are the direction's accumulators (ignored for a control direction).  Requires nv == NV, nc == NC.
-template <int NV, int NC, class Out>
-HD void wb_s3_tangent(const WbModel& md, const WbKnot<NV, NC>& k, const float* contact, int is_u, int dir, const float* t1,
-                      const float* t2, const float* e, const float* h, const float* dfeet, Out out) {
+// element i of a per-thread vector interleaved across the threads of a CTA in shared memory ([i][thread])
+struct WbStrided {
+  float* p;
+  int stride;
+  HD float& operator[](int i) const { return p[i * stride]; }
+};
+
+template <int NV, int NC, class V1, class V2, class Out>
+HD void wb_s3_tangent(const WbModel& md, const WbKnot<NV, NC>& k, const float* contact, int is_u, int dir, V1 t1, V2 t2,
+                      V2 e, V2 h, V2 dfeet, Out out) {
   constexpr int NF = 3 * NC, NJ = NV - 6, NQ = NV + 1;
   float dgrf[NF], xa[NV];
   const int kv = (!is_u && dir >= NQ) ? dir - NQ : -1;  // velocity direction index
@@ -972,6 +979,7 @@ HD void wb_s3_tangent(const WbModel& md, const WbKnot<NV, NC>& k, const float* c
 #pragma unroll
       for (int i = 0; i < NV; ++i) s = fmaf(-k.J[i * NF + c], xw[i], s);
       if (!is_u) {
+#pragma unroll
         for (int i = 0; i < NV; ++i) s = fmaf(-k.MiJ[i * NF + c], e[i], s);
         if (kv >= 0) s = fmaf(-2.f * md.alpha, k.J[kv * NF + c], s);
       }

@@ -63,13 +63,12 @@ __device__ __forceinline__ Dual wb_pen(float c, float sgn, float alpha, float si
 template <int NV, int NC, int NT>
 __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
                                                     const float* sx, const float* su, float* sgrad, const float* satv,
-                                                    float* sG, WbCostSmem<NV, NC>& cs) {
+                                                    float* sG, WbCostSmem<NV, NC>& cs, const float* ref) {
   constexpr int NJ = NV - 6, NF = 3 * NC;
   const int tid = threadIdx.x;
   const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
   const bool term = (t == N);
   const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
-  const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
   const float* W = io.W + size_t(e) * io.w_stride;
   const int nw = md.nw;
   const float* contact = ref + 13 + nj + nf;
@@ -214,12 +213,15 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
       const float w3 = cj * Wc[3 * nw], w4 = cj * Wc[4 * nw], w5 = cj * Wc[5 * nw];
       for (int i = 3; i < 7; ++i) Qc[i * n] = sG[i - 3] * w3 + sG[4 + i - 3] * w4 + sG[8 + i - 3] * w5;
     }
+#pragma unroll 8
     for (int i = 7; i < 13 + 2 * nj; ++i) {
       float s = cj * Wc[(i - 1) * nw];
       if (i == j) s += curv_speed;
       Qc[i * n] = s;
     }
+#pragma unroll 4
     for (int i = 13 + 2 * nj; i < g0; ++i) Qc[i * n] = cs.rc[i] * cj * Wc[(i - 1) * nw];
+#pragma unroll 4
     for (int i = g0; i < n; ++i) {
       float s = cj * Wc[(i - 1 + nj) * nw];
       if (cj_foot >= 0 && (i - g0) / 3 == cj_foot) s = fmaf(hcone * jf3[i - g0 - 3 * cj_foot], jfj, s);
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
 
-  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sgrad, satv, sG, sm.cs);
+  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sgrad, satv, sG, sm.cs, ref);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -399,6 +401,8 @@ template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   WbKnot<NV, NC> k;
   WbTree<NB, NV, NC, NI> tr;
   WbCostSmem<NV, NC> cs;
+  float sref[13 + NJ + 7 * NC];
+  float fold[2 * NV + 2 * NF][NT];  // per-thread t2 | e | h | dfeet of the direction (keeps them out of registers)
   float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
 };
 
@@ -429,6 +433,10 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     satv[i] = 0.f;
   }
   for (int i = tid; i < m; i += NT) { su[i] = term ? 0.f : Ut[i]; satv[n + i] = 0.f; }
+  {
+    const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
+    for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
+  }
   __syncthreads();
 
   if (!term) {
@@ -456,7 +464,9 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     float* A = o.A + (size_t(e) * N + t) * n * n;
     float* B = o.B + (size_t(e) * N + t) * n * m;
     if (tid < NDS + m) {
-      float t1[NV], t2[NV], ee[NV], hh[3 * NC], dfeet[3 * NC];
+      float t1[NV];
+      const WbStrided t2{&sm.fold[0][tid], NT}, ee{&sm.fold[NV][tid], NT}, hh{&sm.fold[2 * NV][tid], NT},
+          dfeet{&sm.fold[2 * NV + 3 * NC][tid], NT};
       const int is_u = tid >= NDS;
       if (!is_u)
         wb_tree_fold(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, tid, t1, t2, ee, hh, dfeet);
@@ -475,7 +485,7 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
   }
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
-  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sm.sgrad, satv, sm.sG, sm.cs);
+  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sm.sgrad, satv, sm.sG, sm.cs, sm.sref);
 }
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction

@@ -311,10 +311,10 @@ HD void wb_tree_items(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, int lane, i
 
 // ---- stage 7: folded tangents of one x-direction `col` (0..nq+nv-1) -- the vectors WbTangentSink accumulates in v2.
 // y, grf, wvz, J are the primal vectors of the knot (WbKnot).  Outputs must have NV / 3 NC entries.
-template <int NB, int NV, int NC, int NI>
+template <int NB, int NV, int NC, int NI, class V1, class V2>
 HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const float* J, const float* w, const float* a,
-                     const float* z, const float* y, const float* grf, const float* wvz, int col, float* t1, float* t2,
-                     float* e, float* h, float* dfeet) {
+                     const float* z, const float* y, const float* grf, const float* wvz, int col, V1 t1, V2 t2, V2 e, V2 h,
+                     V2 dfeet) {
   constexpr int NF = 3 * NC;
 #pragma unroll
   for (int i = 0; i < NV; ++i) { t1[i] = 0.f; t2[i] = 0.f; e[i] = 0.f; }
