@@ -177,6 +177,7 @@ def run_native(args):
     from mpx_b200 import _lib
     from mpx_b200.utils.mpc_wrapper import BatchedMPCControllerWrapper
     from mpx_b200.utils.mpc_wrapper_srbd import BatchedMPCControllerWrapper as SrbdWrapper
+    from mpx_b200.utils.sharding import gather_controls, max_over_ranks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,6 +197,8 @@ def run_native(args):
     T = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
     N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
     lm = not args.scan
+    if args.scan:
+        os.environ["MPXB_LQ"] = "scan"  # bind the associative-scan kernel literally (wrappers default to the sequential one)
 
     if srbd:
         wrap = SrbdWrapper(cfg, E, device=dev)
@@ -287,10 +290,7 @@ def run_native(args):
     lib.mpxb_profile_destroy(prof)
     nonfinite_envs = int((~torch.isfinite(X).flatten(1).all(1)).sum().item())
     alpha_hist = torch.bincount(solver.alpha_index.to(torch.int64), minlength=11).tolist()
-    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_total = float(tms.item())
+    ms_total = max_over_ranks(ms_total, device=dev)
 
     # ---- end to end through the wrapper API with HOST buffers (H2D of x0 / command, D2H of the torques every step)
     e2e = None
@@ -318,19 +318,15 @@ def run_native(args):
             d2 = tick(d2)
         e1.record()
         barrier()
-        t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": E * world * K / (float(t_e2e.item()) * 1e-3), "unit": UNIT,
+        t_e2e = max_over_ranks(e0.elapsed_time(e1), device=dev)
+        e2e = {"value": E * world * K / (t_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(E * (n + 7) * 4), "d2h_bytes_per_step": int(E * nj * 4),
-               "ms_per_step": float(t_e2e.item()) / K,
+               "ms_per_step": t_e2e / K,
                "api": "BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
 
     # final gather of the controls (the only collective; north_star), outside the timed solve path
     if world > 1:
-        tau = U[:, 0, :nj].contiguous()
-        out = [torch.empty_like(tau) for _ in range(world)] if rank == 0 else None
-        dist.gather(tau, out, dst=0)
+        gather_controls(U[:, 0, :nj].contiguous(), n_env_total=E * world, dst=0)
 
     if rank == 0:
         peaks = {}
@@ -359,6 +355,9 @@ def run_native(args):
                     "hbm": {"achieved": blq / lq_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                             "frac": (blq / lq_s / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
                             "algorithmic": f"{lq_bytes(n, m, N) / 1e6:.3f} MB per solve (LQ data read once + outputs written once)"},
+                    "whole_step": {"achieved": flq / (ms_total / K * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                   "frac": flq / (ms_total / K * 1e-3) / 1e12 / fp32_peak,
+                                   "note": "SURVEY.md 8(d): F_lqr x solves/s / FP32 peak over the whole tick (linearise + LQ + line search + shift)"},
                     "kernel_ms": kernel_ms, "dominant_kernel": dom,
                     "share_of_step": {k: v / (ms_total / K) for k, v in kernel_ms.items()}}
         cpu_baseline = None

@@ -107,8 +107,13 @@ void mpxb_model_destroy(mpxb_model* model);
  * in one vmap and keeps the first accepted one (optimizers.py:518-572).  By default libmpxb evaluates alpha = 1
  * first and the ten smaller steps only for environments whose alpha = 1 point is rejected -- X, U, V and
  * alpha_index are identical, but the workspace views "ls_theta" / "ls_phi" then hold entries 1..10 only for
- * those environments.  Set to 1 to evaluate all 11 points for every environment (diagnostics / parity tests). */
-enum { MPXB_OPT_EAGER_LINE_SEARCH = 1 };
+ * those environments.  Set to 1 to evaluate all 11 points for every environment (diagnostics / parity tests).
+ * MPXB_OPT_LINE_SEARCH (default MPXB_LS_FILTER): MPXB_LS_FILTER is parallel_filter_line_search, the search the
+ * reference's mpc runs (optimizers.py:468-578, 670-681); MPXB_LS_MERIT is parallel_line_search on the augmented
+ * Lagrangian merit g + sum((V + rho/2 c) c) with merit_rho / slope (optimizers.py:185-217, 295-354), the call the
+ * reference keeps commented out at optimizers.py:637-669. */
+enum { MPXB_OPT_EAGER_LINE_SEARCH = 1, MPXB_OPT_LINE_SEARCH = 2 };
+enum { MPXB_LS_FILTER = 0, MPXB_LS_MERIT = 1 };
 int mpxb_model_set_option(mpxb_model* model, int option, int value);
 
 /* Bytes of device scratch one mpxb_mpc_step call with E environments needs. */

@@ -31,6 +31,11 @@ struct TrialOut {
   float *theta_k, *phi_k;
   int32_t* need;
   int ia0, nia;
+  // merit-function line search (optimizers.py:185-217, 295-354, 637-669), selected by MPXB_OPT_LINE_SEARCH: every
+  // trial point also needs vc = sum((V + alpha dV) * c_new); trial point 0 adds sum(V c), sum(dV^2), sum(dV c)
+  int merit;
+  const float* dV;
+  float *ls_vc, *vc_k, *dv2, *dvc;
 };
 
 #if defined(__CUDACC__)
@@ -49,13 +54,30 @@ __device__ __forceinline__ bool filter_accept(float theta_new, float phi_new, fl
   return case1 || case2 || case3;
 }
 
+// Merit line search: rho (merit_rho, optimizers.py:185-198), the current merit g + sum((V + rho/2 c) c) and its slope
+// sum(q dX) + sum(r dU) + 2 sum(dV c) - rho sum(c c) (optimizers.py:201-217)
+__device__ __forceinline__ void merit_terms(float theta_k, float phi_k, float vc_k, float dv2, float dvc, float slope_lq,
+                                            float* rho, float* merit_k, float* mslope) {
+  *rho = (theta_k > 1e-12f) ? 2.f * sqrtf(dv2 / theta_k) : 1e-2f;
+  *merit_k = phi_k + vc_k + 0.5f * *rho * theta_k;
+  *mslope = slope_lq + 2.f * dvc - *rho * theta_k;
+}
+// parallel_line_search's step_acceptance (True = the Armijo test FAILS); a NaN merit is replaced by the current one
+__device__ __forceinline__ bool merit_rejected(float theta_new, float phi_new, float vc_new, float rho, float merit_k,
+                                               float mslope, float alpha) {
+  float mn = phi_new + vc_new + 0.5f * rho * theta_new;
+  if (mn != mn) mn = merit_k;
+  return mn > merit_k + alpha * 1e-4f * mslope;
+}
+
 // Tail of the trial kernels (one warp per (env, trial point)): store theta / phi; trial point 0 adds theta_k, phi_k
 // of the current iterate (fixed-order warp reduction: deterministic) and the lazy-evaluation flag.
 __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& o, int e, int ia, int lane, int n,
-                                             float theta, float phi) {
+                                             float theta, float phi, float vc) {
   if (lane == 0) {
     o.ls_theta[e * NALPHA + ia] = theta;
     o.ls_phi[e * NALPHA + ia] = phi;
+    if (o.merit) o.ls_vc[e * NALPHA + ia] = vc;
   }
   if (ia != 0) return;
   const int N = io.N;
@@ -69,10 +91,33 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
     th += __shfl_xor_sync(0xffffffffu, th, s);
     ph += __shfl_xor_sync(0xffffffffu, ph, s);
   }
+  float vk = 0.f, d2 = 0.f, dc = 0.f;
+  if (o.merit) {
+    const float* V = io.V + size_t(e) * nx;
+    const float* dV = o.dV + size_t(e) * nx;
+    for (size_t i = lane; i < nx; i += 32) {
+      vk = fmaf(V[i], c[i], vk);
+      d2 = fmaf(dV[i], dV[i], d2);
+      dc = fmaf(dV[i], c[i], dc);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      vk += __shfl_xor_sync(0xffffffffu, vk, s);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, s);
+      dc += __shfl_xor_sync(0xffffffffu, dc, s);
+    }
+  }
   if (lane == 0) {
     o.theta_k[e] = th;
     o.phi_k[e] = ph;
-    if (o.need) o.need[e] = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
+    if (o.merit) {
+      o.vc_k[e] = vk; o.dv2[e] = d2; o.dvc[e] = dc;
+      float rho, mk, ms;
+      merit_terms(th, ph, vk, d2, dc, o.slope[e], &rho, &mk, &ms);
+      if (o.need) o.need[e] = merit_rejected(theta, phi, vc, rho, mk, ms, 1.f) ? 1 : 0;
+    } else if (o.need) {
+      o.need[e] = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
+    }
   }
 }
 #endif

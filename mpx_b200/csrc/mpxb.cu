@@ -32,6 +32,7 @@ struct mpxb_model {
   SrbdParams srbd;
   WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
   int eager_line_search;  // 1: evaluate all 11 trial points every call (default 0: lazy, same result)
+  int merit_line_search;  // 1: merit-function line search instead of the filter
   WbModel wb_host;
   int device;
 };
@@ -101,6 +102,7 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   mdl->wb_dev = nullptr;
   mdl->prof = nullptr;
   mdl->eager_line_search = 0;
+  mdl->merit_line_search = 0;
   cudaGetDevice(&mdl->device);
   if (d->kind == MPXB_KIND_SRBD) {
     if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
@@ -128,6 +130,11 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
 int mpxb_model_set_option(mpxb_model* m, int option, int value) {
   if (!m) return MPXB_EINVAL;
   if (option == MPXB_OPT_EAGER_LINE_SEARCH) { m->eager_line_search = value ? 1 : 0; return MPXB_OK; }
+  if (option == MPXB_OPT_LINE_SEARCH) {
+    if (value != MPXB_LS_FILTER && value != MPXB_LS_MERIT) return MPXB_EINVAL;
+    m->merit_line_search = (value == MPXB_LS_MERIT);
+    return MPXB_OK;
+  }
   return MPXB_EINVAL;
 }
 
@@ -177,7 +184,8 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost};
     int32_t* need = reinterpret_cast<int32_t*>(ws + L.need);
     TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi, ws + L.c, ws + L.cost, ws + L.slope,
-                ws + L.theta_k, ws + L.phi_k, need, 0, NALPHA};
+                ws + L.theta_k, ws + L.phi_k, need, 0, NALPHA, mdl->merit_line_search, ws + L.dV, ws + L.ls_vc,
+                ws + L.vc_k, ws + L.dv2, ws + L.dvc};
     mpxb_profile* pf = (it == max_iter - 1 && mdl->prof && mdl->prof->calls < mdl->prof->max_calls) ? mdl->prof : nullptr;
     cudaEvent_t* pev = pf ? pf->ev + 5 * pf->calls : nullptr;
     if (pev) cudaEventRecord(pev[0], st);
@@ -220,7 +228,8 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     // K4
     SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.theta_k, ws + L.phi_k, ws + L.ls_theta,
                   ws + L.ls_phi, ws + L.slope, Xn, Un, Vn, ws + L.g, ws + L.last_cost, done, alpha_index, iters,
-                  status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0};
+                  status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0, mdl->merit_line_search, ws + L.ls_vc, ws + L.vc_k,
+                  ws + L.dv2, ws + L.dvc};
     select_update_kernel<<<E, 128, 0, st>>>(sa);
     if (pev) { cudaEventRecord(pev[4], st); pf->calls++; }
     Xc = Xn; Uc = Un; Vc = Vn;
@@ -240,7 +249,7 @@ const float* mpxb_workspace_view(const mpxb_model* mdl, int E, int lq_mode, void
       {"c", L.c, e * (N + 1) * n}, {"K", L.K, e * N * m * n}, {"k", L.k, e * N * m}, {"P", L.P, e * (N + 1) * n * n},
       {"p", L.p, e * (N + 1) * n}, {"dX", L.dX, e * (N + 1) * n}, {"dU", L.dU, e * N * m},
       {"dV", L.dV, e * (N + 1) * n}, {"ls_theta", L.ls_theta, e * NALPHA}, {"ls_phi", L.ls_phi, e * NALPHA},
-      {"g", L.g, e}, {"cost", L.cost, e * (N + 1)}, {"slope", L.slope, e}};
+      {"g", L.g, e}, {"cost", L.cost, e * (N + 1)}, {"slope", L.slope, e}, {"ls_vc", L.ls_vc, e * NALPHA}};
   for (auto& en : ents)
     if (strcmp(en.nm, name) == 0) {
       if (count) *count = en.cnt;

@@ -12,7 +12,7 @@ namespace mpxb {
 // Offsets (in floats) of each per-batch array inside the caller's workspace.
 struct WsLayout {
   size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
-      done, scan, theta_k, phi_k, need, total;
+      done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, total;
 };
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
@@ -51,6 +51,10 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
   L.theta_k = take(e);
   L.phi_k = take(e);
   L.need = take(e);  // int32
+  L.ls_vc = take(e * NALPHA);
+  L.vc_k = take(e);
+  L.dv2 = take(e);
+  L.dvc = take(e);
   L.total = o;
   return L;
 }
@@ -66,6 +70,8 @@ struct SelectArgs {
   int32_t *alpha_index, *iters, *status;  // may be null
   int check_convergence;  // 1 when max_iter > 1
   int first_iter;
+  int merit;  // 1: merit-function line search (parallel_line_search), 0: filter
+  const float *ls_vc, *vc_k, *dv2, *dvc;
 };
 
 // One CTA per env: theta_k, phi_k, filter tests for the 11 trial points, chosen alpha, iterate update.
@@ -93,10 +99,25 @@ __global__ void select_update_kernel(SelectArgs a) {
     // first accepted trial point (largest alpha), else index -1 of the 11 trials (optimizers.py:568-572).  Ascending
     // with early exit: when the line search ran lazily the entries behind the first accepted one were never evaluated.
     int best = NALPHA - 1;
-    for (int i = 0; i < NALPHA; ++i) {
-      if (filter_accept(a.ls_theta[e * NALPHA + i], a.ls_phi[e * NALPHA + i], theta_k, phi_k, slope, exp2f(-float(i)))) {
-        best = i;
-        break;
+    if (a.merit) {
+      // parallel_line_search (optimizers.py:295-354): first trial point that passes the Armijo test on the merit
+      // function; index 0 when none does (argmin of an all-True acceptance vector)
+      float rho, mk, ms;
+      merit_terms(theta_k, phi_k, a.vc_k[e], a.dv2[e], a.dvc[e], slope, &rho, &mk, &ms);
+      best = 0;
+      for (int i = 0; i < NALPHA; ++i) {
+        if (!merit_rejected(a.ls_theta[e * NALPHA + i], a.ls_phi[e * NALPHA + i], a.ls_vc[e * NALPHA + i], rho, mk, ms,
+                            exp2f(-float(i)))) {
+          best = i;
+          break;
+        }
+      }
+    } else {
+      for (int i = 0; i < NALPHA; ++i) {
+        if (filter_accept(a.ls_theta[e * NALPHA + i], a.ls_phi[e * NALPHA + i], theta_k, phi_k, slope, exp2f(-float(i)))) {
+          best = i;
+          break;
+        }
       }
     }
     s_idx = best;

@@ -128,10 +128,12 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
   if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
   const float alpha = exp2f(-float(ia));
   const float* W = io.W + size_t(e) * io.w_stride;
-  float theta = 0.f, phi = 0.f;
+  float theta = 0.f, phi = 0.f, vc = 0.f;
   for (int t = lane; t <= N; t += 32) {
     const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
     const float* dXt = o.dX + (size_t(e) * (N + 1) + t) * n;
+    const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+    const float* dVt = o.merit ? o.dV + (size_t(e) * (N + 1) + t) * n : Vt;
     const float* ref = io.reference + (size_t(e) * (N + 1) + t) * SRBD_NREF;
     const float* par = io.parameter + (size_t(e) * (N + 1) + t) * SRBD_NPAR;
     float x[n], u[m];
@@ -154,6 +156,7 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
       for (int i = 0; i < n; ++i) {
         const float r = xn[i] - fmaf(alpha, dXt[n + i], Xt[n + i]);
         theta = fmaf(r, r, theta);
+        if (o.merit) vc = fmaf(r, fmaf(alpha, dVt[n + i], Vt[n + i]), vc);
       }
     }
     if (t == 0) {
@@ -161,6 +164,7 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
       for (int i = 0; i < n; ++i) {
         const float r = io.x0[size_t(e) * n + i] - x[i];
         theta = fmaf(r, r, theta);
+        if (o.merit) vc = fmaf(r, fmaf(alpha, dVt[i], Vt[i]), vc);
       }
     }
   }
@@ -168,8 +172,9 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
   for (int s = 16; s > 0; s >>= 1) {
     theta += __shfl_xor_sync(0xffffffffu, theta, s);
     phi += __shfl_xor_sync(0xffffffffu, phi, s);
+    vc += __shfl_xor_sync(0xffffffffu, vc, s);
   }
-  trial_finish(io, o, e, ia, lane, n, theta, phi);
+  trial_finish(io, o, e, ia, lane, n, theta, phi, vc);
 }
 
 }  // namespace mpxb

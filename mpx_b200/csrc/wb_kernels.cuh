@@ -510,10 +510,12 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   const int n = md.n, m = md.m;
   const float alpha = exp2f(-float(ia));
   const float* W = io.W + size_t(e) * io.w_stride;
-  float theta = 0.f, phi = 0.f;
+  float theta = 0.f, phi = 0.f, vc = 0.f;
   for (int t = lane; t <= N; t += 32) {
     const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
     const float* dXt = o.dX + (size_t(e) * (N + 1) + t) * n;
+    const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+    const float* dVt = o.merit ? o.dV + (size_t(e) * (N + 1) + t) * n : Vt;
     const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
     const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
     float x[NX], u[NU];
@@ -532,12 +534,14 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
       for (int i = 0; i < n; ++i) {
         const float r = xn[i] - fmaf(alpha, dXt[n + i], Xt[n + i]);
         theta = fmaf(r, r, theta);
+        if (o.merit) vc = fmaf(r, fmaf(alpha, dVt[n + i], Vt[n + i]), vc);
       }
     }
     if (t == 0) {
       for (int i = 0; i < n; ++i) {
         const float r = io.x0[size_t(e) * n + i] - x[i];
         theta = fmaf(r, r, theta);
+        if (o.merit) vc = fmaf(r, fmaf(alpha, dVt[i], Vt[i]), vc);
       }
     }
   }
@@ -545,8 +549,9 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   for (int s = 16; s > 0; s >>= 1) {
     theta += __shfl_xor_sync(0xffffffffu, theta, s);
     phi += __shfl_xor_sync(0xffffffffu, phi, s);
+    vc += __shfl_xor_sync(0xffffffffu, vc, s);
   }
-  trial_finish(io, o, e, ia, lane, n, theta, phi);
+  trial_finish(io, o, e, ia, lane, n, theta, phi, vc);
 }
 
 template <int NV, int NC, int MAXD, int NT>

@@ -35,11 +35,26 @@ def _unwrap(p):
     return p, args
 
 
+def wrapper_lq_is_sequential(limited_memory):
+    """Which LQ kernel the controller wrappers bind.
+
+    The reference picks the associative-scan Riccati (`tvlqr_gpu`) when ``limited_memory=False`` because on an XLA
+    GPU the sequential recursion is launch-latency bound.  Here both forms are single kernels and solve the same LQ
+    problem to rounding; on B200 the sequential kernel is faster for every shipped configuration (measured, E=1:
+    Talos 18.4 ms scan vs. sub-millisecond sequential; SRBD 0.96 ms vs. ~0.1 ms), so the wrappers bind it regardless of
+    ``limited_memory``.  ``MPXB_LQ=scan`` in the environment restores the literal mapping; ``MpcSolver`` itself always
+    maps ``limited_memory`` literally (the parity tests exercise both kernels through it)."""
+    import os
+    if os.environ.get("MPXB_LQ", "").lower() == "scan":
+        return bool(limited_memory)
+    return True
+
+
 class MpcSolver:
     """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
 
     def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None,
-                 eager_line_search=False):
+                 eager_line_search=False, line_search="filter"):
         if not torch.cuda.is_available():
             raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
@@ -58,6 +73,14 @@ class MpcSolver:
         # eager: all 11 trial points for every environment (fills the ls_theta / ls_phi views completely)
         self.eager_line_search = bool(eager_line_search)
         _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_EAGER_LINE_SEARCH, int(self.eager_line_search)),
+                   "mpxb_model_set_option")
+        # "filter": parallel_filter_line_search (what the reference's mpc runs); "merit": parallel_line_search on the
+        # augmented-Lagrangian merit function (optimizers.py:185-217, 295-354, 637-669)
+        if line_search not in ("filter", "merit"):
+            raise ValueError(f"line_search must be 'filter' or 'merit', got {line_search!r}")
+        self.line_search = line_search
+        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_LINE_SEARCH,
+                                                  _lib.LS_MERIT if line_search == "merit" else _lib.LS_FILTER),
                    "mpxb_model_set_option")
         self.ws_bytes = self.lib.mpxb_workspace_bytes(self.handle, self.n_env, self.lq_mode)
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
@@ -129,7 +152,7 @@ class MpcSolver:
         shapes = {"A": (E, N, n, n), "B": (E, N, n, m), "Q": (E, N + 1, n, n), "R": (E, N, m, m), "M": (E, N, n, m),
                   "q": (E, N + 1, n), "r": (E, N, m), "c": (E, N + 1, n), "K": (E, N, m, n), "k": (E, N, m),
                   "P": (E, N + 1, n, n), "p": (E, N + 1, n), "dX": (E, N + 1, n), "dU": (E, N, m),
-                  "dV": (E, N + 1, n), "ls_theta": (E, 11), "ls_phi": (E, 11), "g": (E,), "cost": (E, N + 1),
+                  "dV": (E, N + 1, n), "ls_theta": (E, 11), "ls_phi": (E, 11), "ls_vc": (E, 11), "g": (E,), "cost": (E, N + 1),
                   "slope": (E,)}
         return flat.view(shapes[name])
 

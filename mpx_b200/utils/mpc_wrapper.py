@@ -71,7 +71,8 @@ class _Base:
         self.dynamics = partial(config.dynamics, self.model, None, config.contact_frame, config.body_name,
                                 config.n_joints, config.dt)
         self.work = partial(optimizers.mpc, self.cost, self.dynamics, hessian_approx, limited_memory)
-        self._solver = optimizers.MpcSolver(config, n_env, limited_memory=limited_memory, device=self.device,
+        self._solver = optimizers.MpcSolver(config, n_env, limited_memory=optimizers.wrapper_lq_is_sequential(limited_memory),
+                                            device=self.device,
                                             robot_model=self.model, max_iter=max_iter)
         self.u_ref = self._T(config.u_ref)
         self.W = self._T(config.W)

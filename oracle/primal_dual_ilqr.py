@@ -278,8 +278,52 @@ def parallel_filter_line_search(evaluator, X_in, U_in, V_in, dX, dU, dV, current
     return trials[best]
 
 
-def mpc(cost, dynamics, hessian_approx, limited_memory, reference, parameter, W, x0, X_in, U_in, V_in, detail=None):
+def merit_rho(c, dV):
+    """optimizers.py:185-198."""
+    c2 = torch.sum(c * c)
+    dV2 = torch.sum(dV * dV)
+    return 2.0 * torch.sqrt(dV2 / c2) if bool(c2 > 1e-12) else torch.as_tensor(1e-2, dtype=c.dtype)
+
+
+def merit_slope(dX, dU, dV, c, q, r, rho):
+    """optimizers.py:201-217 (`slope`; note the factor 2 on sum(dV*c), unlike old_optimazers.py:170)."""
+    return torch.sum(q * dX) + torch.sum(r * dU) + 2 * torch.sum(dV * c) - rho * torch.sum(c * c)
+
+
+def parallel_line_search(evaluator, X_in, U_in, V_in, dX, dU, dV, g, c, q, r, armijo_factor=1e-4, detail=None):
+    """optimizers.py:295-354 with the merit function / rho / slope of the (commented-out) call site
+    optimizers.py:637-669: merit = g + sum((V + 0.5 rho c) c), 11 step sizes 2^0..2^-10, Armijo test
+    `merit_new > merit + alpha * armijo * slope` (True = rejected), best = argmin(rejected) if any rejected else 0;
+    a NaN merit is replaced by the current merit."""
+    rho = merit_rho(c, dV)
+    merit_fn = lambda V, g_, c_: g_ + torch.sum((V + 0.5 * rho * c_) * c_)
+    current = merit_fn(V_in, g, c)
+    slope = merit_slope(dX, dU, dV, c, q, r, rho)
+    rejected, trials, merits, thetas, phis, vcs = [], [], [], [], [], []
+    for i in range(11):
+        alpha = 2.0 ** (-i)
+        X_new, U_new, V_new = X_in + alpha * dX, U_in + alpha * dU, V_in + alpha * dV
+        new_g, new_c = evaluator(X_new, U_new)
+        m_new = merit_fn(V_new, new_g, new_c)
+        if bool(torch.isnan(m_new)):
+            m_new = current
+        rejected.append(bool(m_new > current + alpha * armijo_factor * slope))
+        trials.append((X_new, U_new, V_new))
+        merits.append(m_new); thetas.append(torch.sum(new_c * new_c)); phis.append(new_g)
+        vcs.append(torch.sum(V_new * new_c))
+    best = rejected.index(False) if (any(rejected) and not all(rejected)) else 0
+    if detail is not None:
+        detail.update(alpha_index=best, merit=torch.stack(merits), theta=torch.stack(thetas), phi=torch.stack(phis),
+                      vc=torch.stack(vcs), rho=rho, merit_k=current, merit_slope=slope, rejected=rejected)
+    return trials[best]
+
+
+def mpc(cost, dynamics, hessian_approx, limited_memory, reference, parameter, W, x0, X_in, U_in, V_in, detail=None,
+        line_search="filter"):
     """optimizers.py:603-683: one real-time SQP iteration.
+
+    ``line_search="merit"`` selects the augmented-Lagrangian merit line search that the reference keeps (commented
+    out) beside the filter search: optimizers.py:637-669.
 
     ``cost(W, reference, x, u, t)``, ``hessian_approx(W, reference, x, u, t)``,
     ``dynamics(x, u, t, parameter)`` as the reference's partials leave them.
@@ -293,4 +337,6 @@ def mpc(cost, dynamics, hessian_approx, limited_memory, reference, parameter, W,
                                                 detail=detail)
     if detail is not None:
         detail.update(g=g, c=c, dX=dX, dU=dU, dV=dV)
+    if line_search == "merit":
+        return parallel_line_search(evaluator, X_in, U_in, V_in, dX, dU, dV, g, c, q, r, detail=detail)
     return parallel_filter_line_search(evaluator, X_in, U_in, V_in, dX, dU, dV, g, c, q, r, detail=detail)

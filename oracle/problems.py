@@ -68,11 +68,11 @@ class Problem:
         d = mjx_smooth.kinematics(self.m, torch.as_tensor(qpos, dtype=torch.float64))
         return torch.cat([d.geom_xpos[g] for g in self.contact_id]).numpy()
 
-    def mpc(self, limited_memory, reference, parameter, x0, X, U, V, W=None, detail=None):
+    def mpc(self, limited_memory, reference, parameter, x0, X, U, V, W=None, detail=None, line_search="filter"):
         t = lambda a: torch.as_tensor(np.asarray(a), dtype=self.dtype)
         W = self.W if W is None else t(W)
         out = pdi.mpc(self.cost, self.dynamics, self.hessian_approx, limited_memory, t(reference), t(parameter), W,
-                      t(x0), t(X), t(U), t(V), detail=detail)
+                      t(x0), t(X), t(U), t(V), detail=detail, line_search=line_search)
         return out
 
 

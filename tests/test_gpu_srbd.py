@@ -108,3 +108,30 @@ def test_multi_iteration_device_loop(problem):
     torch.cuda.synchronize()
     assert torch.equal(X, X3) and torch.equal(U, U3) and torch.equal(V, V3)
     assert (three.iters == 3).all()
+
+
+@pytest.mark.parametrize("eager", [True, False])
+@pytest.mark.parametrize("cold", [False, True])
+def test_srbd_merit_line_search_matches_oracle(problem, cold, eager):
+    """MPXB_LS_MERIT: parallel_line_search on the augmented-Lagrangian merit function with merit_rho / slope
+    (optimizers.py:185-217, 295-354; the call the reference keeps commented out at 637-669)."""
+    from mpx_b200.primal_dual_ilqr.optimizers import MpcSolver
+    E = 3
+    inp = synthetic_inputs(problem, E, seed=17, cold_start=cold)
+    # start away from the warm start so that the multipliers and the constraint violation are not trivial
+    rng = np.random.default_rng(5)
+    inp["V0"] = rng.normal(0, 0.5, inp["V0"].shape)
+    inp["X0"] = inp["X0"] + rng.normal(0, 0.02, inp["X0"].shape)
+    solver = MpcSolver(cfg, E, limited_memory=True, eager_line_search=eager, line_search="merit")
+    X, U, V = _run(solver, inp)
+    for e in range(E):
+        det = {}
+        Xo, Uo, Vo = problem.mpc(True, inp["reference"][e], inp["parameter"][e], inp["x0"][e], inp["X0"][e],
+                                 inp["U0"][e], inp["V0"][e], detail=det, line_search="merit")
+        assert int(solver.alpha_index[e]) == det["alpha_index"], (int(solver.alpha_index[e]), det["alpha_index"], det["rejected"])
+        npts = 11 if (eager or det["rejected"][0]) else 1
+        assert _rel(solver.view("ls_vc")[e, :npts].cpu().numpy(), det["vc"].numpy()[:npts]) < 1e-3
+        assert _rel(solver.view("ls_theta")[e, :npts].cpu().numpy(), det["theta"].numpy()[:npts]) < 1e-3
+        assert _rel(X[e].cpu().numpy(), Xo.numpy()) < REL_TOL
+        assert _rel(U[e].cpu().numpy(), Uo.numpy()) < REL_TOL
+        assert _rel(V[e].cpu().numpy(), Vo.numpy()) < REL_TOL
