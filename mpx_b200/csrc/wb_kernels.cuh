@@ -53,22 +53,24 @@ __device__ __forceinline__ Dual wb_pen(float c, float sgn, float alpha, float si
   return p;
 }
 
-// P5 of the linearise kernels: cost value + gradient, q, r and the Gauss-Newton blocks Q, R, M of one knot.
-// sx / su / satv / sgrad / sG live in shared memory; satv holds [A | B]^T V_{t+1}.
+// P5 of the linearise kernels: cost value + gradient, q, r and the Gauss-Newton blocks Q, R, M of one knot, in three
+// parts so that the kernel can overlap them with the dynamics derivatives:
+//   wb_cost_prepare  residuals, quaternion-error Jacobian, residual map, penalty values / slopes   (needs x, u only)
+//   wb_gn_blocks     Q, M, R                                                                       (needs prepare)
+//   wb_cost_finish   y = 0.5 (W_bb + W_bb') r_b, cost, gradient, q_t, r_t                           (needs [A|B]'V)
+// Each part is written for worker `tid` of `NT` (any subset of the CTA's threads).
 //
 // The reference takes jax.grad of the cost (optimizers.py:111-120,165-169 through trajax linearize/quadratize); the
 // cost is 0.5 * sum_blocks r_b' W_bb r_b + penalties (objectives.py:77-125, 204-250, 325-376), every residual is
 // an identity map of one entry of (x, u) except the 3x4 quaternion-error block, so the gradient is assembled in
 // closed form: y = 0.5 (W_bb + W_bb') r_b, grad = (dr/dx)' y + penalty slopes.
-template <int NV, int NC, int NT>
-__device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
-                                                    const float* sx, const float* su, float* sgrad, const float* satv,
-                                                    float* sG, WbCostSmem<NV, NC>& cs, const float* ref) {
+template <int NV, int NC>
+__device__ __forceinline__ void wb_cost_prepare(const WbModel& md, const ModelIO& io, int e, int t, const float* sx,
+                                                const float* su, float* sG, WbCostSmem<NV, NC>& cs, const float* ref,
+                                                int tid, int NT) {
   constexpr int NJ = NV - 6, NF = 3 * NC;
-  const int tid = threadIdx.x;
   const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
   const bool term = (t == N);
-  const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
   const float* W = io.W + size_t(e) * io.w_stride;
   const int nw = md.nw;
   const float* contact = ref + 13 + nj + nf;
@@ -76,10 +78,9 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
   const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
   const bool quad = (md.kind == MPXB_KIND_QUAD_WB);
   const bool masked = quad && !md.swing_tracking;  // contact_map (objectives.py:110-113)
-  // block boundaries of the residual vector
-  const int bb[10] = {0, 3, 6, 6 + nj, 9 + nj, 12 + nj, 12 + 2 * nj, ua0, ua0 + nj, ua0 + nj + nf};
+  (void)N; (void)n; (void)m; (void)nc; (void)nf; (void)term; (void)W; (void)nw; (void)contact; (void)ua0; (void)g0; (void)v0;
+  (void)quad; (void)masked;
   const int nact = term ? 12 + 2 * nj : nw;  // the terminal cost drops the foot / torque / GRF terms
-
   // ---- residuals, the quaternion-error Jacobian, the residual map of every state entry
   for (int a = tid; a < nw; a += NT) {
     float r = 0.f;
@@ -140,7 +141,28 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
     cs.pen[d] = pv;
     cs.dpen[d] = pd;
   }
-  __syncthreads();
+}
+
+template <int NV, int NC>
+__device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
+                                               float* sgrad, const float* satv, const float* sG,
+                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
+  const bool term = (t == N);
+  const float* W = io.W + size_t(e) * io.w_stride;
+  const int nw = md.nw;
+  const float* contact = ref + 13 + nj + nf;
+  const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
+  const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
+  const bool quad = (md.kind == MPXB_KIND_QUAD_WB);
+  const bool masked = quad && !md.swing_tracking;  // contact_map (objectives.py:110-113)
+  (void)N; (void)n; (void)m; (void)nc; (void)nf; (void)term; (void)W; (void)nw; (void)contact; (void)ua0; (void)g0; (void)v0;
+  (void)quad; (void)masked;
+  const float* Vt = io.V + (size_t(e) * (N + 1) + t) * n;
+  // block boundaries of the residual vector
+  const int bb[10] = {0, 3, 6, 6 + nj, 9 + nj, 12 + nj, 12 + 2 * nj, ua0, ua0 + nj, ua0 + nj + nf};
+  const int nact = term ? 12 + 2 * nj : nw;
   // ---- y = 0.5 (W_bb + W_bb') r_b ; cost parts r_a (W_bb r_b)_a
   for (int a = tid; a < nw; a += NT) {
     float s1 = 0.f, s2 = 0.f;
@@ -183,6 +205,24 @@ __device__ __forceinline__ void wb_knot_cost_blocks(const WbModel& md, const Mod
       o.r[(size_t(e) * N + t) * m + i] = gi + satv[n + i];
     }
 
+}
+
+template <int NV, int NC>
+__device__ __forceinline__ void wb_gn_blocks(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
+                                             const float* sx, const float* su, const float* sG,
+                                             const WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
+  const bool term = (t == N);
+  const float* W = io.W + size_t(e) * io.w_stride;
+  const int nw = md.nw;
+  const float* contact = ref + 13 + nj + nf;
+  const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
+  const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
+  const bool quad = (md.kind == MPXB_KIND_QUAD_WB);
+  const bool masked = quad && !md.swing_tracking;  // contact_map (objectives.py:110-113)
+  (void)N; (void)n; (void)m; (void)nc; (void)nf; (void)term; (void)W; (void)nw; (void)contact; (void)ua0; (void)g0; (void)v0;
+  (void)quad; (void)masked;
   // ---- Gauss-Newton blocks Q = Jx^T W Jx (+ penalty curvature), R, M   (objectives.py:127-202, 252-323, 378-450)
   float* Q = o.Q + (size_t(e) * (N + 1) + t) * n * n;
   // columns of the identity-mapped state entries: Q[i][j] = c_i c_j W[a_i][a_j], rows walked block by block
@@ -379,7 +419,10 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
 
-  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sgrad, satv, sG, sm.cs, ref);
+  wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sG, sm.cs, ref, tid, NT);
+  __syncthreads();
+  wb_cost_finish<NV, NC>(md, io, o, e, t, sgrad, satv, sG, sm.cs, ref, tid, NT);
+  wb_gn_blocks<NV, NC>(md, io, o, e, t, sx, su, sG, sm.cs, ref, tid, NT);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -438,6 +481,8 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
   }
   __syncthreads();
+  wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
+  __syncthreads();
 
   if (!term) {
     auto sync = [] { __syncthreads(); };
@@ -463,6 +508,8 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     __syncthreads();
     float* A = o.A + (size_t(e) * N + t) * n * n;
     float* B = o.B + (size_t(e) * N + t) * n * m;
+    // S7: thread d -> column d of [A | B].  The Gauss-Newton blocks follow without a barrier, so the warps that hold
+    // few (or cheap) columns start on them while the position directions are still being folded.
     if (tid < NDS + m) {
       float t1[NV];
       const WbStrided t2{&sm.fold[0][tid], NT}, ee{&sm.fold[NV][tid], NT}, hh{&sm.fold[2 * NV][tid], NT},
@@ -477,15 +524,18 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
                             [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); });
       satv[is_u ? n + tid - NDS : tid] = atv;
     }
+    // the foot / GRF tail of the state does not enter the dynamics
     const int ntail = n - NDS;
     for (int idx = tid; idx < n * ntail; idx += NT) {
       const int i = idx / ntail, j = NDS + idx - i * ntail;
       A[i * n + j] = 0.f;
     }
   }
+  wb_gn_blocks<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
-  wb_knot_cost_blocks<NV, NC, NT>(md, io, o, e, t, sx, su, sm.sgrad, satv, sm.sG, sm.cs, sm.sref);
+  __syncthreads();
+  wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT);
 }
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
