@@ -165,6 +165,17 @@ size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m);
  * Replaces the host-side MuJoCo mj_kinematics + geom_xpos read of mpc_wrapper.py:313-318 / 373-376 (whole-body kinds). */
 int mpxb_wb_foot_positions(const mpxb_model* model, void* stream, int E, const float* qpos, float* feet);
 
+/* whole_body_interface (mpx/utils/mpc_utils.py:275-313; bound by mpc_wrapper_srbd.py:72,153-154): turns the SRBD
+ * controller's ground-reaction forces into joint torques at the whole-body rate.  `model` is a MPXB_KIND_QUAD_WB handle
+ * of the same robot (three joints per leg, contact order = leg order).  qM, qfrc_bias, the foot positions and the foot
+ * Jacobians J [nv, 3 nc] are evaluated at (qpos, qvel);  csa = Kp (foot_ref - feet) + Kd (foot_ref_dot - J' qvel);
+ * tau = contact ? -(J grf)[6:] : qfrc_bias[6:] + (qM pinv(J') csa)[6:]  per leg, with pinv(J') = J (J'J)^-1.
+ * Kp, Kd [3nc, 3nc] shared; qpos [E, nq]; qvel [E, nv]; grf, foot_ref, foot_ref_dot [E, 3nc]; contact [E, nc];
+ * tau [E, nj]; J [E, nv, 3nc] or NULL. */
+int mpxb_whole_body_interface(const mpxb_model* model, void* stream, int E, const float* Kp, const float* Kd,
+                              const float* qpos, const float* qvel, const float* grf, const float* foot_ref,
+                              const float* foot_ref_dot, const float* contact, float* tau, float* J);
+
 /* Gait timer + swing / foothold reference generator, batched over E and stream-ordered: the step immediately before
  * the solve in every wrapper tick.  Replaces timer_run (mpx/utils/mpc_utils.py:7-14), reference_generator (38-144,
  * whole-body kinds) and reference_generator_srbd (146-270, MPXB_KIND_SRBD) as the wrappers call them

@@ -78,6 +78,8 @@ def lib():
     L.mpxb_tvlqr_scan_bytes.restype = sz
     L.mpxb_wb_foot_positions.argtypes = [vp, vp, i32, f32p, f32p]
     L.mpxb_wb_foot_positions.restype = i32
+    L.mpxb_whole_body_interface.argtypes = [vp, vp, i32] + [f32p] * 10
+    L.mpxb_whole_body_interface.restype = i32
     L.mpxb_reference_generator.argtypes = [vp, vp, i32, C.POINTER(Gait), f32p, f32p, i32] + [f32p] * 8
     L.mpxb_reference_generator.restype = i32
     L.mpxb_profile_create.argtypes = [i32, C.POINTER(vp)]

@@ -38,6 +38,13 @@ struct TrialOut {
   float *ls_vc, *vc_k, *dv2, *dvc;
 };
 
+// whole_body_interface (mpc_utils.py:275-313) arguments: see wb_interface_kernel
+struct WbiArgs {
+  int E;
+  const float *Kp, *Kd, *qpos, *qvel, *grf, *foot_ref, *foot_ref_dot, *contact;
+  float *tau, *J;
+};
+
 #if defined(__CUDACC__)
 // The 3-case filter acceptance test of parallel_filter_line_search (optimizers.py:541-566) with JAX's NaN semantics
 __device__ __forceinline__ bool filter_accept(float theta_new, float phi_new, float theta_k, float phi_k, float slope,

@@ -269,6 +269,16 @@ int mpxb_shift_extract(const mpxb_model* mdl, void* stream, int E, int shift, co
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
+int mpxb_whole_body_interface(const mpxb_model* mdl, void* stream, int E, const float* Kp, const float* Kd,
+                              const float* qpos, const float* qvel, const float* grf, const float* foot_ref,
+                              const float* foot_ref_dot, const float* contact, float* tau, float* J) {
+  if (!mdl || !Kp || !Kd || !qpos || !qvel || !grf || !foot_ref || !foot_ref_dot || !contact || !tau || E <= 0)
+    return MPXB_EINVAL;
+  if (mdl->desc.kind != MPXB_KIND_QUAD_WB) return MPXB_EINVAL;
+  WbiArgs a{E, Kp, Kd, qpos, qvel, grf, foot_ref, foot_ref_dot, contact, tau, J};
+  return wb_quad_interface(mdl->wb_host, mdl->wb_dev, a, static_cast<cudaStream_t>(stream));
+}
+
 int mpxb_wb_foot_positions(const mpxb_model* mdl, void* stream, int E, const float* qpos, float* feet) {
   if (!mdl || !qpos || !feet || E <= 0) return MPXB_EINVAL;
   if (mdl->desc.kind == MPXB_KIND_SRBD) return MPXB_EINVAL;

@@ -13,4 +13,8 @@ int wb_quad_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const
   return wb_class_trial<14, 18, 4>(h, dev, io, to, st);
 }
 
+int wb_quad_interface(const WbModel& h, const WbModel* dev, const WbiArgs& a, cudaStream_t st) {
+  return wb_class_interface<14, 18, 4>(h, dev, a, st);
+}
+
 }  // namespace mpxb

@@ -604,6 +604,117 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   trial_finish(io, o, e, ia, lane, n, theta, phi, vc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// whole_body_interface (mpc_utils.py:275-313): SRBD ground-reaction forces -> joint torques at the whole-body rate.
+// One CTA per environment: qM, qfrc_bias, foot positions and foot Jacobians from the tree stages of the linearise
+// kernel, then  csa = Kp (foot_ref - feet) + Kd (foot_ref_dot - J' qvel),
+//   tau_fb = D[6:] + (M pinv(J') csa)[6:]   with pinv(J') = J (J'J)^-1 (J' has full row rank away from leg singularities;
+//                                            the reference's SVD pinv truncates there, this Cholesky form returns NaN),
+//   tau_mpc = -(J grf)[6:],   tau = contact ? tau_mpc : tau_fb   per leg.
+template <int NB, int NV, int NC> struct WbiSmem {
+  static constexpr int NF = 3 * NC;
+  WbTree<NB, NV, NC, 1> tr;
+  float M[NV * NV], D[NV], J[NV * NF], feet[NF], G[NF * NF], gi[NF], csa[NF], x[NF], y[NV], qpos[NV + 1], qvel[NV];
+};
+template <int NB, int NV, int NC, int NT>
+__global__ void __launch_bounds__(NT) wb_interface_kernel(const WbModel* __restrict__ mdp, WbiArgs a) {
+  using S = WbiSmem<NB, NV, NC>;
+  constexpr int NF = S::NF, NJ = NV - 6;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const WbModel& md = *mdp;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < NV + 1; i += NT) sm.qpos[i] = a.qpos[size_t(e) * (NV + 1) + i];
+  for (int i = tid; i < NV; i += NT) sm.qvel[i] = a.qvel[size_t(e) * NV + i];
+  __syncthreads();
+  wb_tree_fk(md, sm.tr, sm.qpos, sm.qvel, tid, NT);
+  __syncthreads();
+  wb_tree_bodies(md, sm.tr, sm.qpos, sm.feet, tid, NT);
+  __syncthreads();
+  wb_tree_composite(md, sm.tr, tid, NT);
+  __syncthreads();
+  wb_tree_dofs(md, sm.tr, sm.D, tid, NT);
+  __syncthreads();
+  wb_tree_mass_jac(md, sm.tr, sm.M, sm.J, tid, NT);
+  __syncthreads();
+  const float* Kp = a.Kp;
+  const float* Kd = a.Kd;
+  // cartesian-space action and G = J'J
+  for (int c = tid; c < NF; c += NT) {
+    float s = 0.f;
+    for (int k = 0; k < NF; ++k) {
+      float ld = 0.f;
+      for (int i = 0; i < NV; ++i) ld = fmaf(sm.J[i * NF + k], sm.qvel[i], ld);
+      s = fmaf(Kp[c * NF + k], a.foot_ref[size_t(e) * NF + k] - sm.feet[k], s);
+      s = fmaf(Kd[c * NF + k], a.foot_ref_dot[size_t(e) * NF + k] - ld, s);
+    }
+    sm.csa[c] = s;
+  }
+  for (int idx = tid; idx < NF * NF; idx += NT) {
+    const int r = idx / NF, c = idx - r * NF;
+    float s = 0.f;
+    for (int i = 0; i < NV; ++i) s = fmaf(sm.J[i * NF + r], sm.J[i * NF + c], s);
+    sm.G[idx] = s;
+  }
+  if (a.J)
+    for (int idx = tid; idx < NV * NF; idx += NT) a.J[size_t(e) * NV * NF + idx] = sm.J[idx];
+  __syncthreads();
+  if (tid == 0) {  // 12 x 12 Cholesky solve: x = (J'J)^-1 csa
+    for (int j = 0; j < NF; ++j) {
+      float d = sm.G[j * NF + j];
+      for (int p = 0; p < j; ++p) d = fmaf(-sm.G[j * NF + p], sm.G[j * NF + p], d);
+      const float inv = 1.f / sqrtf(d);
+      sm.gi[j] = inv;
+      for (int i = j + 1; i < NF; ++i) {
+        float v = sm.G[i * NF + j];
+        for (int p = 0; p < j; ++p) v = fmaf(-sm.G[i * NF + p], sm.G[j * NF + p], v);
+        sm.G[i * NF + j] = v * inv;
+      }
+    }
+    for (int i = 0; i < NF; ++i) {
+      float v = sm.csa[i];
+      for (int p = 0; p < i; ++p) v = fmaf(-sm.G[i * NF + p], sm.x[p], v);
+      sm.x[i] = v * sm.gi[i];
+    }
+    for (int i = NF - 1; i >= 0; --i) {
+      float v = sm.x[i];
+      for (int p = i + 1; p < NF; ++p) v = fmaf(-sm.G[p * NF + i], sm.x[p], v);
+      sm.x[i] = v * sm.gi[i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < NV; i += NT) {
+    float s = 0.f;
+    for (int c = 0; c < NF; ++c) s = fmaf(sm.J[i * NF + c], sm.x[c], s);
+    sm.y[i] = s;
+  }
+  __syncthreads();
+  for (int j = tid; j < NJ; j += NT) {
+    float my = 0.f, jg = 0.f;
+    for (int i = 0; i < NV; ++i) my = fmaf(sm.M[(6 + j) * NV + i], sm.y[i], my);
+    for (int c = 0; c < NF; ++c) jg = fmaf(sm.J[(6 + j) * NF + c], a.grf[size_t(e) * NF + c], jg);
+    const float mask = a.contact[size_t(e) * NC + j / 3];  // leg-major joints, three per leg (mpc_utils.py:308)
+    a.tau[size_t(e) * NJ + j] = -jg * mask + (1.f - mask) * (sm.D[6 + j] + my);
+  }
+}
+
+template <int NB, int NV, int NC>
+inline int wb_class_interface(const WbModel& h, const WbModel* dev, const WbiArgs& a, cudaStream_t st) {
+  constexpr int NT = 64;
+  using S = WbiSmem<NB, NV, NC>;
+  if (!h.tree_ok || h.nbody > NB || h.nv != NV || h.nc != NC || h.nj != 3 * NC) return MPXB_EUNSUPPORTED;
+  auto kern = wb_interface_kernel<NB, NV, NC, NT>;
+  static bool configured[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 64 && !configured[d]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
+    configured[d] = true;
+  }
+  kern<<<a.E, NT, sizeof(S), st>>>(dev, a);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
 template <int NV, int NC, int MAXD, int NT>
 inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
   using S = WbLinSmem<NV, NC, MAXD, NT>;

@@ -10,6 +10,7 @@ namespace mpxb {
 
 int wb_quad_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st, int force_v2);
 int wb_quad_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st);
+int wb_quad_interface(const WbModel& h, const WbModel* dev, const WbiArgs& a, cudaStream_t st);
 int wb_h1_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st, int force_v2);
 int wb_h1_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st);
 int wb_talos_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st, int force_v2);

@@ -87,14 +87,54 @@ class BatchedMPCControllerWrapper:
             contact_torch = torch.ones(self.n_env, self.config.n_contact, device=self.device)
         return self.run(x0_torch, input_torch, foot_op_torch, contact_torch)
 
-    def whole_body_run(self, qpos, qvel):
-        raise NotImplementedError("whole_body_interface (mpc_utils.py:275-313) is outside the solve path (SURVEY.md 8f-3)")
+    def _whole_body_model(self):
+        """Whole-body (MJCF tree) handle of the same robot for whole_body_interface, created on first use."""
+        if getattr(self, "_wb_handle", None) is None:
+            import ctypes as C
+            from types import SimpleNamespace
+            cfg = self.config
+            nj, nc = cfg.n_joints, cfg.n_contact
+            wb = SimpleNamespace(model_path=cfg.model_path, contact_frame=cfg.contact_frame, body_name=cfg.body_name,
+                                 n_joints=nj, n_contact=nc, n=13 + 2 * nj + 6 * nc, m=nj, N=cfg.N, dt=cfg.dt,
+                                 W=np.zeros((12 + 3 * nj + 6 * nc,) * 2), dynamics=mpc_dyn_model.quadruped_wb_dynamics,
+                                 cost=mpc_objectives.quadruped_wb_obj)
+            self._wb_desc = _lib.make_desc(wb)
+            handle = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().mpxb_model_create(C.byref(self._wb_desc), C.byref(handle)), "mpxb_model_create")
+            self._wb_handle = handle
+            self._Kp, self._Kd = self._T(cfg.Kp).contiguous(), self._T(cfg.Kd).contiguous()
+        return self._wb_handle
+
+    def whole_body_run(self, qpos, qvel, return_jacobian=False):
+        """mpc_wrapper_srbd.py:153-154 -> mpc_utils.whole_body_interface (275-313) on the device: joint torques
+        [n_env, n_joints] from the last solve's GRFs, foot references and contact schedule."""
+        handle = self._whole_body_model()
+        E, nj, nc = self.n_env, self.config.n_joints, self.config.n_contact
+        qpos, qvel = self._as(qpos).contiguous(), self._as(qvel).contiguous()
+        if tuple(qpos.shape) != (E, 7 + nj) or tuple(qvel.shape) != (E, 6 + nj):
+            raise ValueError(f"qpos / qvel: expected {(E, 7 + nj)} / {(E, 6 + nj)}, got {tuple(qpos.shape)} / {tuple(qvel.shape)}")
+        tau = torch.empty(E, nj, dtype=torch.float32, device=self.device)
+        J = torch.empty(E, 6 + nj, 3 * nc, dtype=torch.float32, device=self.device) if return_jacobian else None
+        grf, fr, frd = self.grf.contiguous(), self.foot_ref.contiguous(), self.foot_ref_dot.contiguous()
+        contact = self._as(self.contact).contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().mpxb_whole_body_interface(
+            handle, stream, E, self._Kp.data_ptr(), self._Kd.data_ptr(), qpos.data_ptr(), qvel.data_ptr(), grf.data_ptr(),
+            fr.data_ptr(), frd.data_ptr(), contact.data_ptr(), tau.data_ptr(), J.data_ptr() if J is not None else None),
+            "mpxb_whole_body_interface")
+        return (tau, J) if return_jacobian else tau
+
+    def torch_whole_body_run(self, qpos, qvel):
+        """mpc_wrapper_srbd.py:156-160 (the tensors already are torch CUDA tensors here)."""
+        return self.whole_body_run(qpos, qvel)
 
     def reset(self, verbose=True):
         """mpc_wrapper_srbd.py:162-174."""
         cfg, E = self.config, self.n_env
         self.contact_time = self._T(cfg.timer_t).repeat(E, 1)
         self.liftoff = torch.zeros(E, 3 * cfg.n_contact, device=self.device)
+        self.contact = torch.ones(E, cfg.n_contact, device=self.device)
         self.batch_U0 = self.u_ref.repeat(E, cfg.N, 1).contiguous()
         self.batch_X0 = self.initial_state.repeat(E, cfg.N + 1, 1).contiguous()
         self.batch_V0 = torch.zeros(E, cfg.N + 1, cfg.n, device=self.device)

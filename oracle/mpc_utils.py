@@ -164,3 +164,22 @@ def reference_generator_srbd(use_terrain_estimator, N, dt, n_contact, mass, foot
     """mpc_utils.py:146-270."""
     return _generator(True, use_terrain_estimator, N, dt, 0, n_contact, mass, foot0, None, t_timer, x, foot, input,
                       duty_factor, step_freq, step_height, liftoff, contact, clearence_speed)
+
+
+def whole_body_interface(m, contact_id, body_id, Kp, Kd, qpos, qvel, grf, foot_ref, foot_ref_dot, contact):
+    """mpc_utils.py:275-313: SRBD ground-reaction forces -> joint torques (torch; ``m`` is the oracle's MJX-style
+    model of oracle/mjx_smooth.py).  Returns (tau [nj], J [nv, 3 nc])."""
+    import torch
+    from . import mjx_smooth
+    d = mjx_smooth.fwd_position(m, qpos)
+    d = mjx_smooth.fwd_velocity(m, d, qvel)
+    M, D = d.qM, d.qfrc_bias
+    legs = [d.geom_xpos[g] for g in contact_id]
+    J = torch.cat([mjx_smooth.jac(m, d, legs[i], body_id[i])[0] for i in range(len(legs))], dim=1)
+    current_leg = torch.cat(legs)
+    current_leg_dot = J.T @ qvel
+    csa = Kp @ (foot_ref - current_leg) + Kd @ (foot_ref_dot - current_leg_dot)
+    tau_fb_lin = D[6:] + (M @ torch.linalg.pinv(J.T) @ csa)[6:]
+    tau_mpc = -(J @ grf)[6:]
+    mask = torch.repeat_interleave(contact, 3)
+    return tau_mpc * mask + (1 - mask) * tau_fb_lin, J
