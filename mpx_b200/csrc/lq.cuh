@@ -34,7 +34,8 @@ template <int n, int m> struct LqSmemLayout {
   static constexpr int oG = oH + LM * LN;    // [LM][LM]
   static constexpr int oK = oG + LM * LM;    // [LM][LN]
   static constexpr int oVec = oK + LM * LN;  // p, w, c, q, h, kk, r, 1/diag(chol G) : 4*LN + 4*LM
-  static constexpr int total = oVec + 4 * LN + 4 * LM + 8;
+  static constexpr int oMR = oVec + 4 * LN + 4 * LM + 8;  // M_t [n][m] and R_t [m][m] prefetched one knot ahead
+  static constexpr int total = oMR + n * m + m * m;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
   // resident CTAs per SM that shared memory allows (227 KB usable, 1 KB reserved per CTA), capped at 4
   static constexpr int min_blocks = (232448 / (bytes + 1024)) < 1 ? 1 : ((232448 / (bytes + 1024)) > 4 ? 4 : int(232448 / (bytes + 1024)));
@@ -99,10 +100,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // asynchronous copy of the leading `cols` columns of a [rows, gcols] global matrix into a [., ld] shared tile
 __device__ __forceinline__ void cp_async_matrix(float* dst, int ld, const float* src, int rows, int gcols, int cols, int tid,
                                                 int nthreads) {
-  for (int idx = tid; idx < rows * cols; idx += nthreads) {
-    const int i = idx / cols, j = idx - i * cols;
-    cp_async4(dst + i * ld + j, src + i * gcols + j);
+  // column j = tid mod CW with CW the power of two >= cols: no integer division, coalesced row segments
+  int cw = 1, sh = 0;
+  while (cw < cols && cw < nthreads) { cw <<= 1; ++sh; }
+  const int j = tid & (cw - 1), step = nthreads >> sh;
+  if (step == 0) {  // more columns than threads (not reached with the shipped sizes)
+    for (int idx = tid; idx < rows * cols; idx += nthreads) {
+      const int i = idx / cols, jj = idx - i * cols;
+      cp_async4(dst + i * ld + jj, src + i * gcols + jj);
+    }
+    return;
   }
+  if (j < cols)
+    for (int i = tid >> sh; i < rows; i += step) cp_async4(dst + i * ld + j, src + i * gcols + j);
 }
 
 __host__ __device__ constexpr int lq_parts(int rows, int nthreads) {  // lanes that share one row: largest power of two with rows * p <= nthreads
@@ -393,7 +403,9 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   float* sh = sq + LN;         // h [LM]
   float* skk = sh + LM;        // k [LM]
   float* sr = skk + LM;        // r_t [LM]
-  float* sgi = sr + LM;        // reciprocal Cholesky diagonal of G [LM] (inside the + 8 ... see layout)
+  float* sgi = sr + LM;        // reciprocal Cholesky diagonal of G [LM]
+  float* sM = smem + L::oMR;   // M_t [n][m] (global layout)
+  float* sR = sM + n * m;      // R_t [m][m]
   const int e = blockIdx.x;
   const int tid = threadIdx.x;
   if (a.done && a.done[e]) return;
@@ -425,6 +437,8 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   }
   cp_async_matrix(sA, LN, gA + size_t(N - 1) * n * n, n, n, acols, tid, NT);
   cp_async_matrix(sB, LM, gB + size_t(N - 1) * n * m, n, m, m, tid, NT);
+  for (int i = tid; i < n * m; i += NT) cp_async4(sM + i, gM + size_t(N - 1) * n * m + i);
+  for (int i = tid; i < m * m; i += NT) cp_async4(sR + i, gR + size_t(N - 1) * m * m + i);
   cp_async_commit();
   for (int i = tid; i < n; i += NT) { const float v = gq[size_t(N) * n + i]; sp[i] = v; gp[size_t(N) * n + i] = v; }
   for (int idx = tid; idx < n * n; idx += NT) gP[size_t(N) * n * n + idx] = gQ[size_t(N) * n * n + idx];
@@ -497,23 +511,28 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
       cp_async_matrix(sB, LM, gB + size_t(t - 1) * n * m, n, m, m, tid, NT);
     }
     cp_async_commit();
-    // ---- S3: H (columns >= LZ hold no B^T P A part) += M^T ; G = sym(R + G)
+    // ---- S3: H (columns >= LZ hold no B^T P A part) += M^T ; G = sym(R + G)   (M_t, R_t arrived with A_t, B_t)
     for (int idx = tid; idx < m * n; idx += NT) {
-      const int j = idx / m, i = idx - j * m;  // M is [n][m]: coalesced read
-      const float mv = gM[size_t(t) * n * m + idx];
+      const int j = idx / m, i = idx - j * m;  // M is [n][m]
+      const float mv = sM[idx];
       sH[i * LN + j] = (j < LZ ? sH[i * LN + j] : 0.f) + mv;
     }
     for (int idx = tid; idx < m * m; idx += NT) {
       const int i = idx / m, j = idx - i * m;
       if (i <= j) {
-        const float gij = gR[size_t(t) * m * m + i * m + j] + sG[i * LM + j];
-        const float gji = gR[size_t(t) * m * m + j * m + i] + sG[j * LM + i];
+        const float gij = sR[i * m + j] + sG[i * LM + j];
+        const float gji = sR[j * m + i] + sG[j * LM + i];
         const float s = 0.5f * (gij + gji);
         sG[i * LM + j] = s;  // both halves are read only by this thread before being written
         sG[j * LM + i] = s;
       }
     }
     __syncthreads();
+    if (t > 0) {  // M_{t-1}, R_{t-1}: their buffers were last read in S3
+      for (int i = tid; i < n * m; i += NT) cp_async4(sM + i, gM + size_t(t - 1) * n * m + i);
+      for (int i = tid; i < m * m; i += NT) cp_async4(sR + i, gR + size_t(t - 1) * m * m + i);
+      cp_async_commit();
+    }
     // ---- S4: Cholesky G = L L^T in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
     if (tid < 32) {
       for (int j = 0; j < m; ++j) {
