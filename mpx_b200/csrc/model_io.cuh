@@ -36,6 +36,8 @@ struct TrialOut {
   int merit;
   const float* dV;
   float *ls_vc, *vc_k, *dv2, *dvc;
+  // cooperative whole-body trial kernel: per-knot partial sums [E, NALPHA, N+1], reduced by trial_reduce_kernel
+  float *th_part, *ph_part, *vc_part;
 };
 
 // whole_body_interface (mpc_utils.py:275-313) arguments: see wb_interface_kernel
@@ -126,6 +128,33 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
       o.need[e] = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
     }
   }
+}
+
+// Sums the per-knot partials of the cooperative trial kernel (fixed order: lanes stride over knots, xor tree) and
+// finishes like the warp-per-trial kernels.  One warp per (env, trial point of this launch).
+template <int DUMMY>
+__global__ void trial_reduce_kernel(ModelIO io, TrialOut o, int n) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= io.E * o.nia) return;
+  const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
+  if (io.done && io.done[e]) return;
+  if (o.ia0 > 0 && o.need && !o.need[e]) return;
+  const int N = io.N;
+  const size_t base = (size_t(e) * NALPHA + ia) * (N + 1);
+  float theta = 0.f, phi = 0.f, vc = 0.f;
+  for (int t = lane; t <= N; t += 32) {
+    theta += o.th_part[base + t];
+    phi += o.ph_part[base + t];
+    if (o.merit) vc += o.vc_part[base + t];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    theta += __shfl_xor_sync(0xffffffffu, theta, s);
+    phi += __shfl_xor_sync(0xffffffffu, phi, s);
+    vc += __shfl_xor_sync(0xffffffffu, vc, s);
+  }
+  trial_finish(io, o, e, ia, lane, n, theta, phi, vc);
 }
 #endif
 

@@ -815,7 +815,8 @@ template <int NV, int NC> struct WbKnot {
 
 // Cooperative primal contact solve (models.py:93-115 / 146-167 / 206-215): `lane` of `nl` workers, `sync()` between
 // the dependent steps.  Host: lane 0 of 1 with a no-op sync.
-template <int NV, int NC, class Sync>
+// TANGENT = false skips what only the derivative needs (z, wvz, the quat_integrate Jacobians): trial evaluations.
+template <int NV, int NC, bool TANGENT = true, class Sync>
 HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u, const float* contact, int lane,
                      int nl, Sync sync) {
   constexpr int NF = 3 * NC;
@@ -932,7 +933,7 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     k.xn[7 + nj + nv + i] = k.feet[i];
     if (md.grf_as_state) k.xn[7 + nj + nv + nf + i] = k.grf[i];
   }
-  for (int s = lane; s < 8; s += nl) {
+  for (int s = (TANGENT ? lane : 7 + lane); s < 8; s += nl) {
     if (s < 7) {
       Dual q[4], om[3], qo[4];
       for (int i = 0; i < 4; ++i) q[i] = Dual(x[3 + i], s == i ? 1.f : 0.f);

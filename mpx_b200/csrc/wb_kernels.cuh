@@ -143,6 +143,28 @@ __device__ __forceinline__ void wb_cost_prepare(const WbModel& md, const ModelIO
   }
 }
 
+// cost value only (trial evaluations): cs.part[a] = r_a (W_bb r_b)_a for the active residual rows
+template <int NV, int NC>
+__device__ __forceinline__ void wb_cost_rowsums(const WbModel& md, const ModelIO& io, int e, int t, WbCostSmem<NV, NC>& cs,
+                                                int tid, int NT) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  const int nj = NJ, nf = NF, nw = md.nw;
+  const float* W = io.W + size_t(e) * io.w_stride;
+  const int ua0 = 12 + 2 * nj + nf;
+  const int bb[10] = {0, 3, 6, 6 + nj, 9 + nj, 12 + nj, 12 + 2 * nj, ua0, ua0 + nj, ua0 + nj + nf};
+  const int nact = (t == io.N) ? 12 + 2 * nj : nw;
+  for (int a = tid; a < nw; a += NT) {
+    float s1 = 0.f;
+    if (a < nact) {
+      int blk = 0;
+#pragma unroll
+      for (int k = 1; k < 9; ++k) blk += (a >= bb[k]) ? 1 : 0;
+      for (int b = bb[blk]; b < bb[blk + 1]; ++b) s1 = fmaf(W[a * nw + b], cs.r[b], s1);
+    }
+    cs.part[a] = cs.r[a] * s1;
+  }
+}
+
 template <int NV, int NC>
 __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
                                                float* sgrad, const float* satv, const float* sG,
@@ -754,11 +776,127 @@ inline int wb_class_linearize(const WbModel& h, const WbModel* dev, const ModelI
   if (h.tree_ok && !force_v2 && h.nbody <= NB && h.nitems <= NI) return wb_launch_linearize3_t<NB, NV, NC, NI, NT>(h, dev, io, lo, st);
   return wb_launch_linearize_t<NV, NC, MAXD, NT>(h, dev, io, lo, st);
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative trial evaluation: one CTA per (env, trial point, knot).  The tree stages and the contact solve of the
+// linearise kernel evaluate x+ = f(x, u) at (X, U) + alpha (dX, dU) with 64 workers instead of one thread with
+// kilobytes of local memory; the closed-form residual machinery of the cost stage gives the cost value.  Per-knot
+// partials of theta = sum c_new^2, phi = sum cost and (merit mode) sum (V + alpha dV) c_new go to the workspace and
+// are summed by trial_reduce_kernel.
+template <int NB, int NV, int NC> struct WbTrialSmem {
+  static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF;
+  WbKnot<NV, NC> k;
+  WbTree<NB, NV, NC, 1> tr;
+  WbCostSmem<NV, NC> cs;
+  float sx[NX], su[NU], sxn[NX], svn[NX], sref[13 + NJ + 7 * NC], sG[12], red[3][2];
+};
+
+template <int NB, int NV, int NC, int NT>
+__global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
+  using S = WbTrialSmem<NB, NV, NC>;
+  constexpr int NQ = NV + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const WbModel& md = *mdp;
+  const int tid = threadIdx.x;
+  const int N = io.N;
+  const int per_env = o.nia * (N + 1);
+  const int e = blockIdx.x / per_env, rem = blockIdx.x - e * per_env;
+  const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
+  if (io.done && io.done[e]) return;
+  if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
+  const int n = md.n, m = md.m;
+  const bool term = (t == N);
+  const float alpha = exp2f(-float(ia));
+  const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
+  const float* dXt = o.dX + (size_t(e) * (N + 1) + t) * n;
+  const float* par = io.parameter + (size_t(e) * (N + 1) + t) * md.npar;
+  for (int i = tid; i < n; i += NT) {
+    sm.sx[i] = fmaf(alpha, dXt[i], Xt[i]);
+    if (!term) {
+      sm.sxn[i] = fmaf(alpha, dXt[n + i], Xt[n + i]);
+      if (o.merit) {
+        const size_t vi = (size_t(e) * (N + 1) + t + 1) * n + i;
+        sm.svn[i] = fmaf(alpha, o.dV[vi], io.V[vi]);
+      }
+    }
+  }
+  for (int i = tid; i < m; i += NT)
+    sm.su[i] = term ? 0.f : fmaf(alpha, o.dU[(size_t(e) * N + t) * m + i], io.U[(size_t(e) * N + t) * m + i]);
+  {
+    const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
+    for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
+  }
+  __syncthreads();
+  // ---- cost value: residuals + penalties, then 0.5 (sum_a r_a (W_bb r_b)_a + sum pen)
+  wb_cost_prepare<NV, NC>(md, io, e, t, sm.sx, sm.su, sm.sG, sm.cs, sm.sref, tid, NT);
+  __syncthreads();
+  wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid, NT);
+  float theta = 0.f, vc = 0.f;
+  if (!term) {
+    wb_tree_fk(md, sm.tr, sm.sx, sm.sx + NQ, tid, NT);
+    __syncthreads();
+    wb_tree_bodies(md, sm.tr, sm.sx, sm.k.feet, tid, NT);
+    __syncthreads();
+    wb_tree_composite(md, sm.tr, tid, NT);
+    __syncthreads();
+    wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
+    __syncthreads();
+    wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
+    __syncthreads();
+    wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
+    for (int i = tid; i < n; i += NT) {
+      const float r = sm.k.xn[i] - sm.sxn[i];
+      theta = fmaf(r, r, theta);
+      if (o.merit) vc = fmaf(r, sm.svn[i], vc);
+    }
+  }
+  if (t == 0)
+    for (int i = tid; i < n; i += NT) {
+      const float r = io.x0[size_t(e) * n + i] - sm.sx[i];
+      theta = fmaf(r, r, theta);
+      if (o.merit) vc = fmaf(r, fmaf(alpha, o.dV[size_t(e) * (N + 1) * n + i], io.V[size_t(e) * (N + 1) * n + i]), vc);
+    }
+  float phi = 0.f;
+  for (int a = tid; a < md.nw; a += NT) phi += sm.cs.part[a];
+  for (int d = tid; d < n + m; d += NT) phi += sm.cs.pen[d];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    theta += __shfl_xor_sync(0xffffffffu, theta, s);
+    phi += __shfl_xor_sync(0xffffffffu, phi, s);
+    vc += __shfl_xor_sync(0xffffffffu, vc, s);
+  }
+  if ((tid & 31) == 0 && (tid >> 5) < 2) { sm.red[0][tid >> 5] = theta; sm.red[1][tid >> 5] = phi; sm.red[2][tid >> 5] = vc; }
+  __syncthreads();
+  if (tid == 0) {
+    const size_t idx = (size_t(e) * NALPHA + ia) * (N + 1) + t;
+    o.th_part[idx] = sm.red[0][0] + sm.red[0][1];
+    o.ph_part[idx] = 0.5f * (sm.red[1][0] + sm.red[1][1]);
+    if (o.merit) o.vc_part[idx] = sm.red[2][0] + sm.red[2][1];
+  }
+}
+
 template <int NB, int NV, int NC>
 inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
-  const int wpb = 2;
-  const int blocks = (io.E * to.nia + wpb - 1) / wpb;
-  wb_trial_kernel<NB, NV, NC><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+  static const int legacy = [] { const char* v = getenv("MPXB_WB_TRIAL"); return (v && v[0] == '1') ? 1 : 0; }();
+  if (legacy || !h.tree_ok || h.nbody > NB) {
+    const int wpb = 2;
+    const int blocks = (io.E * to.nia + wpb - 1) / wpb;
+    wb_trial_kernel<NB, NV, NC><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
+    return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+  }
+  constexpr int NT = 64;
+  using S = WbTrialSmem<NB, NV, NC>;
+  auto kern = wb_trial3_kernel<NB, NV, NC, NT>;
+  static bool configured[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 64 && !configured[d]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
+    configured[d] = true;
+  }
+  kern<<<io.E * to.nia * (io.N + 1), NT, sizeof(S), st>>>(dev, io, to);
+  const int wpb = 4;
+  trial_reduce_kernel<0><<<(io.E * to.nia + wpb - 1) / wpb, wpb * 32, 0, st>>>(io, to, h.n);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
