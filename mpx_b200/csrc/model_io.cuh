@@ -38,7 +38,20 @@ struct TrialOut {
   float *ls_vc, *vc_k, *dv2, *dvc;
   // cooperative whole-body trial kernel: per-knot partial sums [E, NALPHA, N+1], reduced by trial_reduce_kernel
   float *th_part, *ph_part, *vc_part;
+  // second pass of the lazy search: how many environments rejected alpha = 1 decides ON THE DEVICE which of the two
+  // whole-body trial kernels does the work (few -> the cooperative one, many -> one warp per trial point); both are
+  // launched, the one whose condition fails exits at once.  sel: 0 run, 1 run iff *need_count <= thr, 2 iff > thr
+  int32_t* need_count;
+  int sel, thr;
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ bool trial_selected(const TrialOut& o) {
+  if (o.sel == 0) return true;
+  const int c = *o.need_count;
+  return (o.sel == 1) ? (c <= o.thr) : (c > o.thr);
+}
+#endif
 
 // whole_body_interface (mpc_utils.py:275-313) arguments: see wb_interface_kernel
 struct WbiArgs {
@@ -119,13 +132,18 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
   if (lane == 0) {
     o.theta_k[e] = th;
     o.phi_k[e] = ph;
+    int nd = 0;
     if (o.merit) {
       o.vc_k[e] = vk; o.dv2[e] = d2; o.dvc[e] = dc;
       float rho, mk, ms;
       merit_terms(th, ph, vk, d2, dc, o.slope[e], &rho, &mk, &ms);
-      if (o.need) o.need[e] = merit_rejected(theta, phi, vc, rho, mk, ms, 1.f) ? 1 : 0;
-    } else if (o.need) {
-      o.need[e] = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
+      nd = merit_rejected(theta, phi, vc, rho, mk, ms, 1.f) ? 1 : 0;
+    } else {
+      nd = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;
+    }
+    if (o.need) {
+      o.need[e] = nd;
+      if (nd && o.need_count) atomicAdd(o.need_count, 1);  // a count: the order of the increments does not matter
     }
   }
 }
@@ -136,7 +154,7 @@ template <int DUMMY>
 __global__ void trial_reduce_kernel(ModelIO io, TrialOut o, int n) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (warp >= io.E * o.nia) return;
+  if (warp >= io.E * o.nia || !trial_selected(o)) return;
   const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
   if (io.done && io.done[e]) return;
   if (o.ia0 > 0 && o.need && !o.need[e]) return;

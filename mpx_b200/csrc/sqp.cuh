@@ -12,7 +12,7 @@ namespace mpxb {
 // Offsets (in floats) of each per-batch array inside the caller's workspace.
 struct WsLayout {
   size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
-      done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, th_part, ph_part, vc_part, total;
+      done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, th_part, ph_part, vc_part, need_count, total;
 };
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
@@ -58,6 +58,7 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
   L.th_part = take(e * NALPHA * (N + 1));
   L.ph_part = take(e * NALPHA * (N + 1));
   L.vc_part = take(e * NALPHA * (N + 1));
+  L.need_count = take(1);  // int32
   L.total = o;
   return L;
 }

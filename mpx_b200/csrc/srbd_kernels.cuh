@@ -122,7 +122,7 @@ __global__ void srbd_trial_kernel(SrbdParams P, ModelIO io, TrialOut o) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int N = io.N;
-  if (warp >= io.E * o.nia) return;
+  if (warp >= io.E * o.nia || !trial_selected(o)) return;
   const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
   if (io.done && io.done[e]) return;
   if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at

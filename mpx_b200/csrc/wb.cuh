@@ -811,6 +811,8 @@ template <int NV, int NC> struct WbKnot {
   float dL[NV], dLc[NF], D[NV]  /* dL, dLc: reciprocal Cholesky diagonals */, tmd[NV], w[NV], a[NV], z[NV], wvz[NV];
   float y[NF], grf[NF], feet[NF];
   float xn[NX], Gq[16], Gw[12];
+  // explicit-inverse variant (quadruped kernels only, NV <= 18): L^-1 and the right-hand side of the GRF solve
+  float Li[NV <= 18 ? NV * NV : NV], yr[NF];
 };
 
 // Cooperative primal contact solve (models.py:93-115 / 146-167 / 206-215): `lane` of `nl` workers, `sync()` between
@@ -950,6 +952,242 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     }
   }
   sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Explicit-inverse variant of the contact solve (v3 linearise kernel, cooperative trial kernel).  Same quantities as
+// wb_s3_primal, but after the two Cholesky factorisations the inverses qM^-1 = L^-T L^-1 and (J'M^-1J)^-1 are formed
+// once per knot (k.M and k.JMJ then hold the full symmetric inverses), so that every later solve -- M^-1 J, w, the
+// GRFs, and the two qM solves + one contact solve PER COLUMN of [A | B] in wb_s3_tangent_inv -- is a mat-vec with
+// independent accumulators instead of a 300-deep dependent FMA chain.  The chains were what bounded those stages
+// (12 warps per SM cannot hide them).
+template <int NV, int NC, bool TANGENT = true, class Sync>
+HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u, const float* contact,
+                         int lane, int nl, Sync sync) {
+  constexpr int NF = 3 * NC;
+  const int nv = md.nv, nj = md.nj, nf = 3 * md.nc;
+  const float* qvel = x + 7 + nj;
+  for (int i = lane; i < nv; i += nl) k.tmd[i] = (i < 6 ? 0.f : u[i - 6]) - k.D[i];
+  sync();
+  // Cholesky of qM, one column per step; every worker recomputes the pivot so a single barrier per column suffices
+  for (int j = 0; j < nv; ++j) {
+    float sjj = k.M[j * NV + j];
+    for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
+    const float dj = 1.f / sqrtf(sjj);
+    for (int i = j + 1 + lane; i < nv; i += nl) {
+      float s = k.M[i * NV + j];
+      for (int p = 0; p < j; ++p) s = fmaf(-k.M[i * NV + p], k.M[j * NV + p], s);
+      k.M[i * NV + j] = s * dj;
+    }
+    if (lane == 0) k.dL[j] = dj;
+    sync();
+  }
+  // L^-1, one column per worker
+  for (int j = lane; j < nv; j += nl) {
+    k.Li[j * NV + j] = k.dL[j];
+    for (int i = j + 1; i < nv; ++i) {
+      float s = 0.f;
+      for (int p = j; p < i; ++p) s = fmaf(k.M[i * NV + p], k.Li[p * NV + j], s);
+      k.Li[i * NV + j] = -s * k.dL[i];
+    }
+  }
+  sync();
+  // qM^-1 = L^-T L^-1 (full symmetric) over the factor
+  for (int idx = lane; idx < nv * nv; idx += nl) {
+    const int i = idx / nv, j = idx - i * nv;
+    float s = 0.f;
+    for (int q = (i > j ? i : j); q < nv; ++q) s = fmaf(k.Li[q * NV + i], k.Li[q * NV + j], s);
+    k.M[i * NV + j] = s;
+  }
+  sync();
+  if (md.contact_solve) {
+    for (int idx = lane; idx < nv * nf + nv; idx += nl) {
+      if (idx < nv * nf) {
+        const int i = idx / nf, c = idx - i * nf;
+        float s = 0.f;
+        for (int q = 0; q < nv; ++q) s = fmaf(k.M[i * NV + q], k.J[q * NF + c], s);
+        k.MiJ[i * NF + c] = s;
+      } else {
+        const int i = idx - nv * nf;
+        float s = 0.f;
+        for (int q = 0; q < nv; ++q) s = fmaf(k.M[i * NV + q], k.tmd[q], s);
+        k.w[i] = s;
+      }
+    }
+    sync();
+    for (int idx = lane; idx < nf * nf + nf; idx += nl) {
+      if (idx < nf * nf) {
+        const int a = idx / nf, b = idx - a * nf;
+        if (b <= a) {
+          float s = 0.f;
+          for (int i = 0; i < nv; ++i) s = fmaf(k.J[i * NF + a], k.MiJ[i * NF + b], s);
+          if (a == b) s += md.reg;
+          k.JMJ[a * NF + b] = s;
+        }
+      } else {
+        const int a = idx - nf * nf;
+        float s = 0.f;
+        for (int i = 0; i < nv; ++i) s = fmaf(k.J[i * NF + a], k.w[i] + 2.f * md.alpha * qvel[i], s);
+        k.yr[a] = -s;
+      }
+    }
+    sync();
+    for (int j = 0; j < nf; ++j) {
+      float sjj = k.JMJ[j * NF + j];
+      for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
+      const float dj = 1.f / sqrtf(sjj);
+      for (int i = j + 1 + lane; i < nf; i += nl) {
+        float s = k.JMJ[i * NF + j];
+        for (int p = 0; p < j; ++p) s = fmaf(-k.JMJ[i * NF + p], k.JMJ[j * NF + p], s);
+        k.JMJ[i * NF + j] = s * dj;
+      }
+      if (lane == 0) k.dLc[j] = dj;
+      sync();
+    }
+    // the contact system stays a Cholesky solve: for H1's regularised line contacts (models.py:155-157) an explicit
+    // inverse of J'M^-1J loses three digits
+    if (lane == 0) {
+      float yy[NF];
+#pragma unroll
+      for (int c = 0; c < NF; ++c) yy[c] = k.yr[c];
+      wb_tri_solve<NF>(k.JMJ, NF, k.dLc, yy);
+#pragma unroll
+      for (int c = 0; c < NF; ++c) { k.y[c] = yy[c]; k.grf[c] = yy[c] * contact[c / 3]; }
+    }
+    sync();
+    for (int i = lane; i < nv; i += nl) {
+      float sz = 0.f, sa = k.w[i];
+      for (int c = 0; c < nf; ++c) { sz = fmaf(k.MiJ[i * NF + c], k.y[c], sz); sa = fmaf(k.MiJ[i * NF + c], k.grf[c], sa); }
+      k.z[i] = sz;
+      k.a[i] = sa;
+      k.wvz[i] = k.w[i] + 2.f * md.alpha * qvel[i] + sz;
+    }
+  } else {
+    for (int c = lane; c < nf; c += nl) { k.grf[c] = u[nj + c] * contact[c / 3]; k.y[c] = 0.f; }
+    for (int i = lane; i < nv; i += nl) { k.w[i] = 0.f; k.z[i] = 0.f; k.wvz[i] = 0.f; }
+    sync();
+    for (int i = lane; i < nv; i += nl) {  // tmd <- tau - D + J grf, then a = qM^-1 tmd
+      float s = k.tmd[i];
+      for (int c = 0; c < nf; ++c) s = fmaf(k.J[i * NF + c], k.grf[c], s);
+      k.Li[i] = s;  // L^-1 is dead: scratch
+    }
+    sync();
+    for (int i = lane; i < nv; i += nl) {
+      float s = 0.f;
+      for (int q = 0; q < nv; ++q) s = fmaf(k.M[i * NV + q], k.Li[q], s);
+      k.a[i] = s;
+    }
+  }
+  sync();
+  // semi-implicit Euler step and the Jacobians of quat_integrate wrt (quat, omega+)
+  const float dt = md.dt;
+  float* vn = k.xn + 7 + nj;
+  for (int i = lane; i < nv; i += nl) vn[i] = qvel[i] + k.a[i] * dt;
+  sync();
+  for (int i = lane; i < 3; i += nl) k.xn[i] = x[i] + vn[i] * dt;
+  for (int i = lane; i < nj; i += nl) k.xn[7 + i] = x[7 + i] + vn[6 + i] * dt;
+  for (int i = lane; i < nf; i += nl) {
+    k.xn[7 + nj + nv + i] = k.feet[i];
+    if (md.grf_as_state) k.xn[7 + nj + nv + nf + i] = k.grf[i];
+  }
+  for (int s = (TANGENT ? lane : 7 + lane); s < 8; s += nl) {
+    if (s < 7) {
+      Dual q[4], om[3], qo[4];
+      for (int i = 0; i < 4; ++i) q[i] = Dual(x[3 + i], s == i ? 1.f : 0.f);
+      for (int i = 0; i < 3; ++i) om[i] = Dual(vn[3 + i], s == 4 + i ? 1.f : 0.f);
+      quat_integrate(q, om, dt, qo);
+      for (int r = 0; r < 4; ++r) {
+        if (s < 4) k.Gq[r * 4 + s] = qo[r].d;
+        else k.Gw[r * 3 + s - 4] = qo[r].d;
+      }
+    } else {
+      float qo[4];
+      quat_integrate(x + 3, vn + 3, dt, qo);
+      for (int r = 0; r < 4; ++r) k.xn[3 + r] = qo[r];
+    }
+  }
+  sync();
+}
+
+// wb_s3_tangent on what wb_s3_primal_inv leaves: k.M = qM^-1 (explicit), k.JMJ / k.dLc = Cholesky factor of J'M^-1J
+template <int NV, int NC, class V1, class V2, class Out>
+HD void wb_s3_tangent_inv(const WbModel& md, const WbKnot<NV, NC>& k, const float* contact, int is_u, int dir, V1 t1, V2 t2,
+                          V2 e, V2 h, V2 dfeet, Out out) {
+  constexpr int NF = 3 * NC, NJ = NV - 6, NQ = NV + 1;
+  float dgrf[NF], xa[NV];
+  const int kv = (!is_u && dir >= NQ) ? dir - NQ : -1;  // velocity direction index
+  if (md.contact_solve) {
+    float xw[NV], rhs[NF];
+    if (is_u) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xw[i] = k.M[i * NV + 6 + dir];  // qM^-1 e_{6+dir}
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) s = fmaf(k.M[i * NV + q], t1[q], s);
+        xw[i] = s;  // dw
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      float s = is_u ? 0.f : -h[c];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s = fmaf(-k.J[i * NF + c], xw[i], s);
+      if (!is_u) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s = fmaf(-k.MiJ[i * NF + c], e[i], s);
+        if (kv >= 0) s = fmaf(-2.f * md.alpha, k.J[kv * NF + c], s);
+      }
+      rhs[c] = s;
+    }
+    wb_tri_solve<NF>(k.JMJ, NF, k.dLc, rhs);
+#pragma unroll
+    for (int c = 0; c < NF; ++c) dgrf[c] = rhs[c] * contact[c / 3];
+  } else {
+#pragma unroll
+    for (int c = 0; c < NF; ++c) dgrf[c] = (is_u && dir == NJ + c) ? contact[c / 3] : 0.f;
+  }
+  {
+    float xr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float s = is_u ? ((i == 6 + dir && dir < NJ) ? 1.f : 0.f) : t2[i];
+#pragma unroll
+      for (int c = 0; c < NF; ++c) s = fmaf(k.J[i * NF + c], dgrf[c], s);
+      xr[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) s = fmaf(k.M[i * NV + q], xr[q], s);
+      xa[i] = s;  // da
+    }
+  }
+  const float dt = md.dt;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xa[i] = ((i == kv) ? 1.f : 0.f) + dt * xa[i];  // d v+
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out(i, ((!is_u && dir == i) ? 1.f : 0.f) + dt * xa[i]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float s = (!is_u && dir >= 3 && dir < 7) ? k.Gq[r * 4 + dir - 3] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s = fmaf(k.Gw[r * 3 + c], xa[3 + c], s);
+    out(3 + r, s);
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) out(7 + i, ((!is_u && dir == 7 + i) ? 1.f : 0.f) + dt * xa[6 + i]);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out(NQ + i, xa[i]);
+#pragma unroll
+  for (int c = 0; c < NF; ++c) out(NQ + NV + c, is_u ? 0.f : dfeet[c]);
+  if (md.grf_as_state) {
+#pragma unroll
+    for (int c = 0; c < NF; ++c) out(NQ + NV + NF + c, dgrf[c]);
+  }
 }
 
 // One column of [A | B] from the folded tangents of one direction (see WbTangentSink), handed entry by entry to

@@ -518,7 +518,9 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     __syncthreads();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
-    wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
+    // explicit qM^-1 pays for the 18-dof quadrupeds (no spills, shorter chains); measured slower for H1 / Talos
+    if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
+    else wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
     {
       float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
       const float* Xn = Xt + n;
@@ -542,8 +544,9 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       float atv = 0.f;
       float* dst = is_u ? B + (tid - NDS) : A + tid;
       const int ld = is_u ? m : n;
-      wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet,
-                            [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); });
+      auto sink = [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); };
+      if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
+      else wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
       satv[is_u ? n + tid - NDS : tid] = atv;
     }
     // the foot / GRF tail of the state does not enter the dynamics
@@ -575,7 +578,7 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int N = io.N;
-  if (warp >= io.E * o.nia) return;
+  if (warp >= io.E * o.nia || !trial_selected(o)) return;
   const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
   if (io.done && io.done[e]) return;
   if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
@@ -802,6 +805,7 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
   const int per_env = o.nia * (N + 1);
   const int e = blockIdx.x / per_env, rem = blockIdx.x - e * per_env;
   const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
+  if (!trial_selected(o)) return;
   if (io.done && io.done[e]) return;
   if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
   const int n = md.n, m = md.m;
@@ -843,7 +847,8 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     __syncthreads();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
-    wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
+    if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
+    else wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
     for (int i = tid; i < n; i += NT) {
       const float r = sm.k.xn[i] - sm.sxn[i];
       theta = fmaf(r, r, theta);
@@ -876,27 +881,41 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
 }
 
 template <int NB, int NV, int NC>
-inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to, cudaStream_t st) {
+inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to_in, cudaStream_t st) {
   static const int legacy = [] { const char* v = getenv("MPXB_WB_TRIAL"); return (v && v[0] == '1') ? 1 : 0; }();
-  if (legacy || !h.tree_ok || h.nbody > NB) {
+  // the cooperative kernel wins for the quadrupeds at any batch size and for every robot when the batch is too small
+  // to fill the GPU with one warp per trial point (single-instance latency); measured slower for H1 x2048
+  const bool coop_ok = !legacy && h.tree_ok && h.nbody <= NB && (NV <= 18 || io.E * (io.N + 1) <= 148 * 8);
+  TrialOut to = to_in;
+  // first pass / eager evaluation: cooperative (if available) resp. warp-per-trial; second pass: both, selected on the
+  // device by the number of environments that still need the smaller steps
+  const bool second = to.ia0 > 0 && to.need_count != nullptr;
+  const bool run_warp = !coop_ok || second || to.nia == NALPHA;
+  const bool run_coop = coop_ok && to.nia != NALPHA;
+  to.thr = io.E / 8;
+  if (run_warp) {
+    to.sel = (second && coop_ok) ? 2 : 0;
     const int wpb = 2;
     const int blocks = (io.E * to.nia + wpb - 1) / wpb;
     wb_trial_kernel<NB, NV, NC><<<blocks, wpb * 32, 0, st>>>(dev, io, to);
-    return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+    if (cudaGetLastError() != cudaSuccess) return MPXB_ECUDA;
   }
-  constexpr int NT = 64;
-  using S = WbTrialSmem<NB, NV, NC>;
-  auto kern = wb_trial3_kernel<NB, NV, NC, NT>;
-  static bool configured[64] = {};
-  int d = 0;
-  cudaGetDevice(&d);
-  if (d < 64 && !configured[d]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
-    configured[d] = true;
+  if (run_coop) {
+    to.sel = second ? 1 : 0;
+    constexpr int NT = 64;
+    using S = WbTrialSmem<NB, NV, NC>;
+    auto kern = wb_trial3_kernel<NB, NV, NC, NT>;
+    static bool configured[64] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 64 && !configured[d]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
+      configured[d] = true;
+    }
+    kern<<<io.E * to.nia * (io.N + 1), NT, sizeof(S), st>>>(dev, io, to);
+    const int wpb = 4;
+    trial_reduce_kernel<0><<<(io.E * to.nia + wpb - 1) / wpb, wpb * 32, 0, st>>>(io, to, h.n);
   }
-  kern<<<io.E * to.nia * (io.N + 1), NT, sizeof(S), st>>>(dev, io, to);
-  const int wpb = 4;
-  trial_reduce_kernel<0><<<(io.E * to.nia + wpb - 1) / wpb, wpb * 32, 0, st>>>(io, to, h.n);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 

@@ -94,7 +94,8 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   wb_tree_composite(md, tr, 0, 1);
   wb_tree_dofs(md, tr, k.D, 0, 1);
   wb_tree_mass_jac(md, tr, k.M, k.J, 0, 1);
-  wb_s3_primal<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
+  if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
+  else wb_s3_primal<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
   for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
   wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
   wb_tree_items(md, tr, 0, 1, nosync);
@@ -104,7 +105,9 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
     const int is_u = d >= nq + nv;
     if (!is_u) wb_tree_fold(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, d, t1, t2, e, h, dfeet);
     float* cp = col.data();
-    wb_s3_tangent<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
+    if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
+                          [cp](int i, float v) { cp[i] = v; });
+    else wb_s3_tangent<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
     for (int i = 0; i < n; ++i) {
       if (!is_u) A[i * n + d] = col[i];
