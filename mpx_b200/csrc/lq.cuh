@@ -41,6 +41,45 @@ template <int n, int m> struct LqSmemLayout {
   static constexpr int min_blocks = (232448 / (bytes + 1024)) < 1 ? 1 : ((232448 / (bytes + 1024)) > 4 ? 4 : int(232448 / (bytes + 1024)));
 };
 
+// Layout of lq_seq_kernel's arena for a given number of live columns of A (LZ = pad4(nzc)): A and T1 = P A only
+// need LZ columns, Q_t is staged unpadded ([n][n], odd stride) over T1.  For the whole-body quadrupeds (n = 61,
+// nzc = 37) this is 56 KB instead of 67 KB, i.e. four resident CTAs per SM instead of three.
+struct LqRtLayout {
+  int oP, oA, oT, oB, oPB, oH, oG, oK, oVec, oR, total;
+};
+template <int n, int m> __host__ __device__ inline LqRtLayout lq_rt_layout(int LZ) {
+  constexpr int LN = lq_pad(n), LM = lq_pad(m);
+  LqRtLayout o;
+  o.oP = 0;
+  o.oA = LN * LN;                 // [LN][LZ]
+  o.oT = o.oA + LN * LZ;          // T1 [LN][LZ], then Q_t [n][n]
+  const int szT = (LN * LZ > lq_pad(n * n)) ? LN * LZ : lq_pad(n * n);
+  o.oB = o.oT + szT;              // [LN][LM]
+  o.oPB = o.oB + LN * LM;         // [LN][LM]
+  o.oH = o.oPB + LN * LM;         // [LM][LN]
+  o.oG = o.oH + LM * LN;          // [LM][LM]
+  o.oK = o.oG + LM * LM;          // [LM][LN]
+  o.oVec = o.oK + LM * LN;        // p, w, c, q [LN]; h, kk, r, 1/diag(chol G) [LM]
+  o.oR = o.oVec + 4 * LN + 4 * LM + 8;  // R_t [m][m], prefetched one knot ahead
+  o.total = o.oR + lq_pad(m * m);
+  return o;
+}
+// resident CTAs per SM (capped at 4) the register allocation is tuned for: the occupancy shared memory allows with
+// the number of live columns of A the shipped whole-body models have (13 + 2 nj of n = 13 + 2 nj + 6 nc [+ 3 nc])
+template <int n, int m> __host__ __device__ constexpr int lq_rt_min_blocks() {
+  constexpr int LN = lq_pad(n), LM = lq_pad(m);
+  constexpr int nzc = (n == 61 && m == 12) ? 37 : (n == 75 && m == 19) ? 51 : (n == 81 && m == 46) ? 57 : n;
+  constexpr int LZ = lq_pad(nzc);
+  constexpr int szT = (LN * LZ > lq_pad(n * n)) ? LN * LZ : lq_pad(n * n);
+  constexpr int total = LN * LN + LN * LZ + szT + 2 * LN * LM + 2 * LM * LN + LM * LM + 4 * LN + 4 * LM + 8 + lq_pad(m * m);
+  constexpr int b = 232448 / (total * 4 + 1024);
+  return b < 1 ? 1 : (b > 4 ? 4 : b);
+}
+template <int n, int m> inline size_t lq_rt_bytes(int nzc) {
+  const int z = (nzc > 0 && nzc < n) ? nzc : n;
+  return size_t(lq_rt_layout<n, m>((z + 3) & ~3).total) * sizeof(float);
+}
+
 // C[MT*4, NT*4] = op(A) * op(B); op(A)(i,k) = TA ? A[k*lda+i] : A[i*lda+k]; op(B)(k,j) = TB ? B[j*ldb+k] : B[k*ldb+j].
 // All dimensions are multiples of 4 (zero padded).  Each thread owns 4x4 tiles tid, tid+nthreads, ...
 template <bool TA, bool TB>
@@ -127,14 +166,16 @@ __host__ __device__ constexpr int lq_parts(int rows, int nthreads) {  // lanes t
 // buffer so a knot costs two shared-memory mat-vecs and three barriers.  dV needs no chain: it is evaluated for all
 // knots at once afterwards, one warp per row of P.  `smem` is the whole (now dead) backward-pass arena.
 template <int n, int m, int NT>
-__device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int tid, float* smem, int acols) {
+__device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int tid, float* smem, int acols, int arena) {
   constexpr int LN = lq_pad(n), LM = lq_pad(m);
   constexpr int PD = lq_parts(m, NT), PX = lq_parts(n, NT);
-  // one stage: K | A (acols wide) | B | q | r | c | k | [P | p when two stages with P still fit the arena]
-  constexpr int ARENA = LqSmemLayout<n, m>::total;
+  // one stage: K | A (acols wide) | B | q | r | c | k | [P | p].  P_t, p_t ride inside both stages when that fits the
+  // arena (pmode 2), else in ONE extra buffer refilled as soon as dV_t is done (pmode 1), else dV is a separate pass
   const int SB0 = 2 * m * n + n * acols + 2 * n + 2 * m;
-  const bool withP = 2 * (SB0 + n * n + n) + 2 * LN + LM + NT / 32 <= ARENA;
-  const int SB = SB0 + (withP ? n * n + n : 0);
+  const int extras = 2 * LN + LM + NT / 32;
+  const int pmode = (2 * (SB0 + n * n + n) + extras <= arena) ? 2 : ((2 * SB0 + n * n + n + extras <= arena) ? 1 : 0);
+  const bool withP = pmode != 0;
+  const int SB = SB0 + (pmode == 2 ? n * n + n : 0);
   const int N = a.N;
   const float* gA = a.A + size_t(e) * N * n * n;
   const float* gB = a.B + size_t(e) * N * n * m;
@@ -149,7 +190,8 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
   float* gdU = a.dU + size_t(e) * N * m;
   float* gdV = a.dV + size_t(e) * (N + 1) * n;
   float* stage = smem;
-  float* sdx = smem + 2 * SB;  // [2][LN]
+  float* sPone = smem + 2 * SB;                               // pmode 1: the single P | p buffer
+  float* sdx = sPone + (pmode == 1 ? n * n + n : 0);          // [2][LN]
   float* sdu = sdx + 2 * LN;   // [LM]
   float* sred = sdu + LM;      // [NT / 32]
   auto prefetch = [&](int t, int buf) {
@@ -162,7 +204,7 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     float* sc = sr + m;
     float* sk = sc + n;
     float* sPm = sk + m;
-    if (withP) {
+    if (pmode == 2) {
       for (int i = tid; i < n * n; i += NT) cp_async4(sPm + i, gP + size_t(t) * n * n + i);
       for (int i = tid; i < n; i += NT) cp_async4(sPm + n * n + i, gp + size_t(t) * n + i);
     }
@@ -173,7 +215,13 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     for (int i = tid; i < m; i += NT) { cp_async4(sr + i, gr + size_t(t) * m + i); cp_async4(sk + i, gk + size_t(t) * m + i); }
     cp_async_commit();
   };
+  auto prefetch_p = [&](int t) {  // pmode 1
+    for (int i = tid; i < n * n; i += NT) cp_async4(sPone + i, gP + size_t(t) * n * n + i);
+    for (int i = tid; i < n; i += NT) cp_async4(sPone + n * n + i, gp + size_t(t) * n + i);
+    cp_async_commit();
+  };
   __syncthreads();  // the backward pass is done with the arena
+  if (pmode == 1) prefetch_p(0);
   prefetch(0, 0);
   for (int i = tid; i < n; i += NT) sdx[i] = gc[i];
   float slope_acc = 0.f;
@@ -186,7 +234,7 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
     const float* sr = sq + n;
     const float* sc = sr + m;
     const float* sk = sc + n;
-    const float* sPm = sk + m;
+    const float* sPm = (pmode == 1) ? sPone : sk + m;
     const float* dx = sdx + (t & 1) * LN;
     float* dxn = sdx + ((t + 1) & 1) * LN;
     if (t + 1 < N) {
@@ -224,6 +272,7 @@ __device__ __forceinline__ void lq_rollout_stream(const LqArgs& a, int e, int ti
       if (row < n && part == 0) gdV[size_t(t) * n + row] = s + sPm[n * n + row];
     }
     __syncthreads();
+    if (pmode == 1 && t + 1 < N) prefetch_p(t + 1);  // every worker is done with P_t
     {  // dx+ = A dx + B du + c : PX lanes per row
       const int row = tid / PX, part = tid - row * PX;
       float s = 0.f;
@@ -384,19 +433,21 @@ __device__ __forceinline__ void tile_store(float* __restrict__ C, int ldc, int i
 //   S7  P = sym(Q + XY)   (pair-owned, conflict-free skewed walk; the reference's inner sym(A^T P A) only reorders
 //       roundings of the same symmetric sum)
 template <int n, int m, int NT>
-__global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_kernel(LqArgs a) {
-  using L = LqSmemLayout<n, m>;
-  constexpr int LN = L::LN, LM = L::LM, TN = LN / 4, TM = LM / 4;
+__global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(LqArgs a) {
+  constexpr int LN = lq_pad(n), LM = lq_pad(m), TN = LN / 4, TM = LM / 4;
   extern __shared__ __align__(16) float smem[];
-  float* sP = smem + L::oP;    // P_{t+1}; X / XY of the step; P_t
-  float* sA = smem + L::oA;    // A_t (leading LZ columns)
-  float* sT = smem + L::oT;    // T1 = P A; then Q_t
-  float* sB = smem + L::oB;    // [LN][LM]
-  float* sPB = smem + L::oPB;  // [LN][LM]
-  float* sH = smem + L::oH;    // [LM][LN]
-  float* sG = smem + L::oG;    // [LM][LM]
-  float* sK = smem + L::oK;    // [LM][LN]
-  float* sp = smem + L::oVec;  // p   [LN]
+  const int nzc = (a.nzc > 0 && a.nzc < n) ? a.nzc : n;
+  const int LZ = (nzc + 3) & ~3, TZ = LZ / 4;
+  const LqRtLayout L = lq_rt_layout<n, m>(LZ);
+  float* sP = smem + L.oP;    // P_{t+1}; X / XY of the step; P_t
+  float* sA = smem + L.oA;    // A_t (leading LZ columns)
+  float* sT = smem + L.oT;    // T1 = P A; then Q_t
+  float* sB = smem + L.oB;    // [LN][LM]
+  float* sPB = smem + L.oPB;  // [LN][LM]
+  float* sH = smem + L.oH;    // [LM][LN]
+  float* sG = smem + L.oG;    // [LM][LM]
+  float* sK = smem + L.oK;    // [LM][LN]
+  float* sp = smem + L.oVec;  // p   [LN]
   float* sw = sp + LN;         // w = p + P c
   float* sc = sw + LN;         // c_{t+1}
   float* sq = sc + LN;         // q_t + A^T w
@@ -404,14 +455,11 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   float* skk = sh + LM;        // k [LM]
   float* sr = skk + LM;        // r_t [LM]
   float* sgi = sr + LM;        // reciprocal Cholesky diagonal of G [LM]
-  float* sM = smem + L::oMR;   // M_t [n][m] (global layout)
-  float* sR = sM + n * m;      // R_t [m][m]
+  float* sR = smem + L.oR;     // R_t [m][m]
   const int e = blockIdx.x;
   const int tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
-  const int nzc = (a.nzc > 0 && a.nzc < n) ? a.nzc : n;
-  const int LZ = (nzc + 3) & ~3, TZ = LZ / 4;
   const int acols = (LZ < n) ? LZ : n;  // columns of A fetched (those in [nzc, LZ) are stored zeros)
   const float* gA = a.A + size_t(e) * N * n * n;
   const float* gB = a.B + size_t(e) * N * n * m;
@@ -427,7 +475,7 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   float* gp = a.p + size_t(e) * (N + 1) * n;
 
   // zero every buffer once: the padding of the cp.async targets is never written again
-  for (int i = tid; i < L::total; i += NT) smem[i] = 0.f;
+  for (int i = tid; i < L.total; i += NT) smem[i] = 0.f;
   __syncthreads();
   // terminal value function: P_N = Q_N, p_N = q_N   (primal_tvlqr.py:136); first A, B
   // (stored transposed: the products below read P^T, and Q_N is the one P that need not be symmetric)
@@ -435,9 +483,8 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
     const int i = idx / n, j = idx - i * n;
     cp_async4(sP + j * LN + i, gQ + size_t(N) * n * n + idx);
   }
-  cp_async_matrix(sA, LN, gA + size_t(N - 1) * n * n, n, n, acols, tid, NT);
+  cp_async_matrix(sA, LZ, gA + size_t(N - 1) * n * n, n, n, acols, tid, NT);
   cp_async_matrix(sB, LM, gB + size_t(N - 1) * n * m, n, m, m, tid, NT);
-  for (int i = tid; i < n * m; i += NT) cp_async4(sM + i, gM + size_t(N - 1) * n * m + i);
   for (int i = tid; i < m * m; i += NT) cp_async4(sR + i, gR + size_t(N - 1) * m * m + i);
   cp_async_commit();
   for (int i = tid; i < n; i += NT) { const float v = gq[size_t(N) * n + i]; sp[i] = v; gp[size_t(N) * n + i] = v; }
@@ -454,8 +501,8 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
       if (tile < TN * TZ) {
         const int i0 = (tile / TZ) * 4, j0 = (tile % TZ) * 4;
         tile_zero(acc);
-        tile_atb(acc, sP, LN, i0, sA, LN, j0, n);
-        tile_store(sT, LN, i0, j0, acc);
+        tile_atb(acc, sP, LN, i0, sA, LZ, j0, n);
+        tile_store(sT, LZ, i0, j0, acc);
       } else if (tile < TN * TZ + TN * TM) {
         const int tt = tile - TN * TZ;
         const int i0 = (tt / TM) * 4, j0 = (tt % TM) * 4;
@@ -476,13 +523,13 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
       if (tile < TZ * TZ) {
         const int i0 = (tile / TZ) * 4, j0 = (tile % TZ) * 4;
         tile_zero(acc);
-        tile_atb(acc, sA, LN, i0, sT, LN, j0, n);
+        tile_atb(acc, sA, LZ, i0, sT, LZ, j0, n);
         tile_store(sP, LN, i0, j0, acc);  // P_{t+1} is dead
       } else if (tile < TZ * TZ + TM * TZ) {
         const int tt = tile - TZ * TZ;
         const int i0 = (tt / TZ) * 4, j0 = (tt % TZ) * 4;
         tile_zero(acc);
-        tile_atb(acc, sB, LM, i0, sT, LN, j0, n);
+        tile_atb(acc, sB, LM, i0, sT, LZ, j0, n);
         tile_store(sH, LN, i0, j0, acc);
       } else if (tile < TZ * TZ + TM * TZ + TM * TM) {
         const int tt = tile - TZ * TZ - TM * TZ;
@@ -499,22 +546,22 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
         const int i = tile - TZ * TZ - TM * TZ - TM * TM - LM;
         float s = (i < n) ? gq[size_t(t) * n + i] : 0.f;
         if (i < LZ)
-          for (int j = 0; j < n; ++j) s = fmaf(sA[j * LN + i], sw[j], s);
+          for (int j = 0; j < n; ++j) s = fmaf(sA[j * LZ + i], sw[j], s);
         sq[i] = s;
       }
     }
     __syncthreads();
     // prefetch: Q_t over T1, A_{t-1} / B_{t-1} over A_t / B_t
-    cp_async_matrix(sT, LN, gQ + size_t(t) * n * n, n, n, n, tid, NT);
+    for (int i = tid; i < n * n; i += NT) cp_async4(sT + i, gQ + size_t(t) * n * n + i);  // unpadded [n][n]
     if (t > 0) {
-      cp_async_matrix(sA, LN, gA + size_t(t - 1) * n * n, n, n, acols, tid, NT);
+      cp_async_matrix(sA, LZ, gA + size_t(t - 1) * n * n, n, n, acols, tid, NT);
       cp_async_matrix(sB, LM, gB + size_t(t - 1) * n * m, n, m, m, tid, NT);
     }
     cp_async_commit();
     // ---- S3: H (columns >= LZ hold no B^T P A part) += M^T ; G = sym(R + G)   (M_t, R_t arrived with A_t, B_t)
     for (int idx = tid; idx < m * n; idx += NT) {
       const int j = idx / m, i = idx - j * m;  // M is [n][m]
-      const float mv = sM[idx];
+      const float mv = gM[size_t(t) * n * m + idx];
       sH[i * LN + j] = (j < LZ ? sH[i * LN + j] : 0.f) + mv;
     }
     for (int idx = tid; idx < m * m; idx += NT) {
@@ -528,8 +575,7 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
       }
     }
     __syncthreads();
-    if (t > 0) {  // M_{t-1}, R_{t-1}: their buffers were last read in S3
-      for (int i = tid; i < n * m; i += NT) cp_async4(sM + i, gM + size_t(t - 1) * n * m + i);
+    if (t > 0) {  // R_{t-1}: its buffer was last read in S3
       for (int i = tid; i < m * m; i += NT) cp_async4(sR + i, gR + size_t(t - 1) * m * m + i);
       cp_async_commit();
     }
@@ -610,8 +656,8 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
       int j = i + d;
       if (j >= LN) j -= LN;
       if ((2 * d == LN && i >= LN / 2) || i >= n || j >= n) continue;
-      const float zij = sT[i * LN + j] + sP[i * LN + j];
-      const float zji = sT[j * LN + i] + sP[j * LN + i];
+      const float zij = sT[i * n + j] + sP[i * LN + j];
+      const float zji = sT[j * n + i] + sP[j * LN + i];
       const float s = 0.5f * (zij + zji);
       sP[i * LN + j] = s;
       sP[j * LN + i] = s;
@@ -626,7 +672,7 @@ __global__ void __launch_bounds__(NT, LqSmemLayout<n, m>::min_blocks) lq_seq_ker
   __syncthreads();
 
   // ---- forward rollout + dual (primal_tvlqr.py:484-498, dual_tvlqr.py:19) ----
-  lq_rollout_stream<n, m, NT>(a, e, tid, smem, acols);
+  lq_rollout_stream<n, m, NT>(a, e, tid, smem, acols, L.total);
 }
 
 }  // namespace mpxb

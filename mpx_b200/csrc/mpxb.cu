@@ -46,11 +46,11 @@ template <int n, int m> cudaError_t launch_lq_seq(const LqArgs& a, cudaStream_t 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LqSmemLayout<n, m>::bytes));
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
     if (err != cudaSuccess) return err;
     configured[dev] = true;
   }
-  kern<<<a.E, NT, LqSmemLayout<n, m>::bytes, st>>>(a);
+  kern<<<a.E, NT, lq_rt_bytes<n, m>(a.nzc), st>>>(a);
   return cudaGetLastError();
 }
 
