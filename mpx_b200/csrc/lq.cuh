@@ -60,7 +60,7 @@ template <int n, int m> __host__ __device__ inline LqRtLayout lq_rt_layout(int L
   o.oG = o.oH + LM * LN;          // [LM][LM]
   o.oK = o.oG + LM * LM;          // [LM][LN]
   o.oVec = o.oK + LM * LN;        // p, w, c, q [LN]; h, kk, r, 1/diag(chol G) [LM]
-  o.oR = o.oVec + 4 * LN + 4 * LM + 8;  // R_t [m][m], prefetched one knot ahead
+  o.oR = o.oVec + 5 * LN + 4 * LM + 8;  // R_t [m][m], prefetched one knot ahead
   o.total = o.oR + lq_pad(m * m);
   return o;
 }
@@ -71,7 +71,7 @@ template <int n, int m> __host__ __device__ constexpr int lq_rt_min_blocks() {
   constexpr int nzc = (n == 61 && m == 12) ? 37 : (n == 75 && m == 19) ? 51 : (n == 81 && m == 46) ? 57 : n;
   constexpr int LZ = lq_pad(nzc);
   constexpr int szT = (LN * LZ > lq_pad(n * n)) ? LN * LZ : lq_pad(n * n);
-  constexpr int total = LN * LN + LN * LZ + szT + 2 * LN * LM + 2 * LM * LN + LM * LM + 4 * LN + 4 * LM + 8 + lq_pad(m * m);
+  constexpr int total = LN * LN + LN * LZ + szT + 2 * LN * LM + 2 * LM * LN + LM * LM + 5 * LN + 4 * LM + 8 + lq_pad(m * m);
   constexpr int b = 232448 / (total * 4 + 1024);
   return b < 1 ? 1 : (b > 4 ? 4 : b);
 }
@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
   float* skk = sh + LM;        // k [LM]
   float* sr = skk + LM;        // r_t [LM]
   float* sgi = sr + LM;        // reciprocal Cholesky diagonal of G [LM]
+  float* sqin = sgi + LM + 8;  // q_t [LN], prefetched one knot ahead (like c_{t+1} in sc and r_t in sr)
   float* sR = smem + L.oR;     // R_t [m][m]
   const int e = blockIdx.x;
   const int tid = threadIdx.x;
@@ -486,13 +487,14 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
   cp_async_matrix(sA, LZ, gA + size_t(N - 1) * n * n, n, n, acols, tid, NT);
   cp_async_matrix(sB, LM, gB + size_t(N - 1) * n * m, n, m, m, tid, NT);
   for (int i = tid; i < m * m; i += NT) cp_async4(sR + i, gR + size_t(N - 1) * m * m + i);
+  for (int i = tid; i < n * m; i += NT) cp_async4(sK + i, gM + size_t(N - 1) * n * m + i);  // M_t rides in K's buffer until S5
+  for (int i = tid; i < n; i += NT) { cp_async4(sc + i, gc + size_t(N) * n + i); cp_async4(sqin + i, gq + size_t(N - 1) * n + i); }
+  for (int i = tid; i < m; i += NT) cp_async4(sr + i, gr + size_t(N - 1) * m + i);
   cp_async_commit();
   for (int i = tid; i < n; i += NT) { const float v = gq[size_t(N) * n + i]; sp[i] = v; gp[size_t(N) * n + i] = v; }
   for (int idx = tid; idx < n * n; idx += NT) gP[size_t(N) * n * n + idx] = gQ[size_t(N) * n * n + idx];
 
   for (int t = N - 1; t >= 0; --t) {
-    for (int i = tid; i < n; i += NT) sc[i] = gc[size_t(t + 1) * n + i];
-    for (int i = tid; i < m; i += NT) sr[i] = gr[size_t(t) * m + i];
     cp_async_wait_all();
     __syncthreads();
     // ---- S1
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
         sh[i] = (i < m) ? s : 0.f;
       } else {
         const int i = tile - TZ * TZ - TM * TZ - TM * TM - LM;
-        float s = (i < n) ? gq[size_t(t) * n + i] : 0.f;
+        float s = (i < n) ? sqin[i] : 0.f;
         if (i < LZ)
           for (int j = 0; j < n; ++j) s = fmaf(sA[j * LZ + i], sw[j], s);
         sq[i] = s;
@@ -556,12 +558,14 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
     if (t > 0) {
       cp_async_matrix(sA, LZ, gA + size_t(t - 1) * n * n, n, n, acols, tid, NT);
       cp_async_matrix(sB, LM, gB + size_t(t - 1) * n * m, n, m, m, tid, NT);
+      for (int i = tid; i < n; i += NT) { cp_async4(sc + i, gc + size_t(t) * n + i); cp_async4(sqin + i, gq + size_t(t - 1) * n + i); }
+      for (int i = tid; i < m; i += NT) cp_async4(sr + i, gr + size_t(t - 1) * m + i);
     }
     cp_async_commit();
     // ---- S3: H (columns >= LZ hold no B^T P A part) += M^T ; G = sym(R + G)   (M_t, R_t arrived with A_t, B_t)
     for (int idx = tid; idx < m * n; idx += NT) {
       const int j = idx / m, i = idx - j * m;  // M is [n][m]
-      const float mv = gM[size_t(t) * n * m + idx];
+      const float mv = sK[idx];  // M_t, staged in K's buffer (K_t is written in S5)
       sH[i * LN + j] = (j < LZ ? sH[i * LN + j] : 0.f) + mv;
     }
     for (int idx = tid; idx < m * m; idx += NT) {
@@ -650,6 +654,10 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
     }
     cp_async_wait_all();
     __syncthreads();
+    if (t > 0) {  // K_t is dead: stage M_{t-1} in its buffer
+      for (int i = tid; i < n * m; i += NT) cp_async4(sK + i, gM + size_t(t - 1) * n * m + i);
+      cp_async_commit();
+    }
     // ---- S7: P = sym(Q + XY): unordered pairs {i, (i + d) mod LN}; lanes walk i, so both accesses hit 32 banks
     for (int idx = tid; idx < (LN / 2 + 1) * LN; idx += NT) {
       const int d = idx / LN, i = idx - d * LN;

@@ -803,11 +803,14 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
   const int tid = threadIdx.x;
   const int N = io.N;
   const int per_env = o.nia * (N + 1);
-  const int e = blockIdx.x / per_env, rem = blockIdx.x - e * per_env;
-  const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
   if (!trial_selected(o)) return;
-  if (io.done && io.done[e]) return;
-  if (o.ia0 > 0 && o.need && !o.need[e]) return;  // alpha = 1 was accepted: the smaller steps are never looked at
+  // grid-stride over the (env, trial point, knot) items: the first pass launches one CTA per item, the second pass a
+  // fixed grid whose CTAs skip the environments that accepted alpha = 1
+  for (int item = blockIdx.x; item < io.E * per_env; item += gridDim.x) {
+  const int e = item / per_env, rem = item - e * per_env;
+  const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
+  if (io.done && io.done[e]) continue;
+  if (o.ia0 > 0 && o.need && !o.need[e]) continue;  // alpha = 1 was accepted: the smaller steps are never looked at
   const int n = md.n, m = md.m;
   const bool term = (t == N);
   const float alpha = exp2f(-float(ia));
@@ -878,6 +881,8 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     o.ph_part[idx] = 0.5f * (sm.red[1][0] + sm.red[1][1]);
     if (o.merit) o.vc_part[idx] = sm.red[2][0] + sm.red[2][1];
   }
+  __syncthreads();  // the next item reuses the shared arrays
+  }
 }
 
 template <int NB, int NV, int NC>
@@ -912,7 +917,8 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
       configured[d] = true;
     }
-    kern<<<io.E * to.nia * (io.N + 1), NT, sizeof(S), st>>>(dev, io, to);
+    const int items = io.E * to.nia * (io.N + 1);
+    kern<<<(second && items > 148 * 32) ? 148 * 32 : items, NT, sizeof(S), st>>>(dev, io, to);
     const int wpb = 4;
     trial_reduce_kernel<0><<<(io.E * to.nia + wpb - 1) / wpb, wpb * 32, 0, st>>>(io, to, h.n);
   }

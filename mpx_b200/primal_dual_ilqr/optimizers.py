@@ -88,7 +88,16 @@ class MpcSolver:
         self.alpha_index = torch.zeros(E, dtype=torch.int32, device=self.device)
         self.iters = torch.zeros(E, dtype=torch.int32, device=self.device)
         self.status = torch.zeros(E, dtype=torch.int32, device=self.device)
-        self.launches_per_call = (4 if self.eager_line_search else 5) * self.max_iter
+        # kernels per SQP iteration: linearise, LQ, select + the trial kernels (eager: one; lazy: alpha = 1, then the rest;
+        # the cooperative whole-body form adds its reduce kernel, and its second pass launches both forms -- see
+        # wb_class_trial in csrc/wb_kernels.cuh)
+        if self.eager_line_search:
+            trial = 1
+        elif self.desc.kind != 0 and (self.desc.nv <= 18 or self.n_env * (self.N + 1) <= 148 * 8):
+            trial = 2 + 3
+        else:
+            trial = 2
+        self.launches_per_call = (3 + trial) * self.max_iter
 
     def __del__(self):
         try:
