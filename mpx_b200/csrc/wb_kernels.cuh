@@ -467,7 +467,10 @@ template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   WbTree<NB, NV, NC, NI> tr;
   WbCostSmem<NV, NC> cs;
   float sref[13 + NJ + 7 * NC];
-  float fold[2 * NV + 2 * NF][NT];  // per-thread t2 | e | h | dfeet of the direction (keeps them out of registers)
+  // folded tangents t1 | t2 | e | h | dfeet of every x-direction ([row][direction], wb_tree_fold_coop) + direction frames
+  static constexpr int FW = 2 * NV + 1;
+  float fold[(3 * NV + 2 * NF) * FW];
+  WbDirW<NV> dw[NV + 1];
   float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
 };
 
@@ -532,15 +535,21 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     __syncthreads();
     float* A = o.A + (size_t(e) * N + t) * n * n;
     float* B = o.B + (size_t(e) * N + t) * n * m;
-    // S7: thread d -> column d of [A | B].  The Gauss-Newton blocks follow without a barrier, so the warps that hold
-    // few (or cheap) columns start on them while the position directions are still being folded.
+    // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
+    // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
+    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync);
+    __syncthreads();
     if (tid < NDS + m) {
+      constexpr int FW = S::FW, NF3 = 3 * NC;
       float t1[NV];
-      const WbStrided t2{&sm.fold[0][tid], NT}, ee{&sm.fold[NV][tid], NT}, hh{&sm.fold[2 * NV][tid], NT},
-          dfeet{&sm.fold[2 * NV + 3 * NC][tid], NT};
       const int is_u = tid >= NDS;
-      if (!is_u)
-        wb_tree_fold(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, tid, t1, t2, ee, hh, dfeet);
+      const int cc = is_u ? 0 : tid;
+      if (!is_u) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) t1[i] = sm.fold[i * FW + cc];
+      }
+      const WbStrided t2{sm.fold + NV * FW + cc, FW}, ee{sm.fold + 2 * NV * FW + cc, FW}, hh{sm.fold + 3 * NV * FW + cc, FW},
+          dfeet{sm.fold + (3 * NV + NF3) * FW + cc, FW};
       float atv = 0.f;
       float* dst = is_u ? B + (tid - NDS) : A + tid;
       const int ld = is_u ? m : n;

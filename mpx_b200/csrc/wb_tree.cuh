@@ -412,4 +412,133 @@ HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const 
   }
 }
 
+// ---- stage 7, cooperative form: the same folded tangents for ALL x-directions of the knot at once, as independent
+// work items instead of one long thread per direction (which kept 19 of 64 lanes busy).
+//   F1  worker per position direction: its frame (S_d, the four X vectors, the three mu, moves / ancestor masks)
+//   F2  items (direction, dof)  -> t1, t2, e   and items (direction, foot) -> h, dfeet
+// Results go to `fold` ([row][col], row = t1 NV | t2 NV | e NV | h 3NC | dfeet 3NC, ld = FW >= nq + nv), from where
+// the column threads of the tangent stage pick them up.
+template <int NV> struct WbDirW {
+  float Sd[6], X[4][6], mu[3][6];
+  uint32_t moves, anc;
+  int b0, nbd, off, pad;
+};
+template <int NB, int NV, int NC, int NI, class Sync>
+HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const float* J, const float* w,
+                          const float* a, const float* z, const float* y, const float* grf, const float* wvz,
+                          WbDirW<NV>* dw, float* fold, int FW, int lane, int nl, Sync sync) {
+  constexpr int NF = 3 * NC, NQ = NV + 1;
+  const int npos = 4 + md.nj, ncol = NQ + md.nv;
+  // F1
+  for (int col = 3 + lane; col < NQ; col += nl) {
+    const int D = col - 3;
+    WbDirW<NV>& d = dw[col];
+    const int b0 = md.dir_b0[D], nbd = md.dir_nb[D], off = md.dir_off[D];
+    const bool isq = D < 4;
+    float Sd[6];
+    const float *vd, *cd;
+    wb_dir_frame(md, tr, D, Sd, vd, cd);
+    float X0[6];
+    motion_cross_force(Sd, tr.Fb[b0], X0);
+    for (int k = 0; k < 6; ++k) { d.Sd[k] = Sd[k]; d.X[0][k] = X0[k] + tr.g[off][k]; }
+    for (int kk = 0; kk < 3; ++kk) {
+      const float* u = (kk == 0) ? w : (kk == 1 ? a : z);
+      float ad[6], t[6], mu[6], Xk[6];
+      if (isq) { ad[0] = ad[1] = ad[2] = 0.f; ad[3] = u[0]; ad[4] = u[1]; ad[5] = u[2]; }
+      else { for (int k = 0; k < 6; ++k) ad[k] = tr.al[kk][b0][k]; }
+      motion_cross(Sd, ad, mu);
+      for (int k = 0; k < 6; ++k) mu[k] = -mu[k];
+      motion_cross_force(Sd, tr.F[kk][b0], Xk);
+      inert_mul(tr.Ic[b0], mu, t);
+      for (int k = 0; k < 6; ++k) { d.mu[kk][k] = mu[k]; d.X[1 + kk][k] = Xk[k] + t[k]; }
+    }
+    uint32_t moves = 0;
+    for (int i = 0; i < md.nv; ++i) {
+      const int bi = md.dof_body[i];
+      if (isq ? (i >= 3) : (bi >= b0 && bi < b0 + nbd)) moves |= 1u << i;
+    }
+    d.moves = moves;
+    d.anc = isq ? 7u : md.dof_anc[D + 2];
+    d.b0 = b0; d.nbd = nbd; d.off = off;
+  }
+  sync();
+  // F2
+  const int nitem1 = ncol * NV, nitem2 = ncol * NC;
+  for (int it = lane; it < nitem1 + nitem2; it += nl) {
+    if (it < nitem1) {
+      const int col = it / NV, i = it - col * NV;
+      float t1 = 0.f, t2 = 0.f, e = 0.f;
+      if (col >= NQ) {  // velocity direction
+        const int D = col - 3, b0 = md.dir_b0[D], nbd = md.dir_nb[D], off = md.dir_off[D];
+        const int bi = md.dof_body[i];
+        float s = 0.f;
+        if (bi >= b0 && bi < b0 + nbd) s = dot6(tr.S[i], tr.g[off + bi - b0]);
+        else if ((md.dof_anc[D - npos] >> i) & 1u) s = dot6(tr.S[i], tr.g[off]);
+        t1 = -s; t2 = -s;
+      } else if (col >= 3 && i < md.nv) {
+        const WbDirW<NV>& d = dw[col];
+        const bool mv = (d.moves >> i) & 1u;
+        if (mv) {
+          const float dD = dot6(tr.S[i], tr.g[d.off + md.dof_body[i] - d.b0]);
+          t1 = -(dD + dot6(tr.U[i], d.mu[0]));
+          t2 = -(dD + dot6(tr.U[i], d.mu[1]));
+          e = -dot6(tr.U[i], d.mu[2]);
+        } else if ((d.anc >> i) & 1u) {
+          const float dD = dot6(tr.S[i], d.X[0]);
+          t1 = -(dD + dot6(tr.S[i], d.X[1]));
+          t2 = -(dD + dot6(tr.S[i], d.X[2]));
+          e = -dot6(tr.S[i], d.X[3]);
+        }
+        for (int c = 0; c < md.nc; ++c) {  // foot Jacobian terms of this dof, feet in fixed order
+          const int bc = md.contact_body[c];
+          if (bc < d.b0 || bc >= d.b0 + d.nbd || !((md.contact_dofmask[c] >> i) & 1u)) continue;
+          float dJ[3];
+          if (mv) {
+            cross3(d.Sd, J + i * NF + 3 * c, dJ);
+          } else {
+            float pc[3];
+            cross3(d.Sd, tr.rc[c], pc);
+            for (int k = 0; k < 3; ++k) pc[k] += d.Sd[3 + k];
+            cross3(tr.S[i], pc, dJ);
+          }
+          for (int k = 0; k < 3; ++k) {
+            t2 = fmaf(dJ[k], grf[3 * c + k], t2);
+            e = fmaf(dJ[k], y[3 * c + k], e);
+          }
+        }
+      }
+      fold[i * FW + col] = t1;
+      fold[(NV + i) * FW + col] = t2;
+      fold[(2 * NV + i) * FW + col] = e;
+    } else {
+      const int it2 = it - nitem1;
+      const int col = it2 / NC, c = it2 - col * NC;
+      float hc[3] = {0.f, 0.f, 0.f}, df[3] = {0.f, 0.f, 0.f};
+      if (col < 3) {
+        df[col] = 1.f;
+      } else if (col < NQ && c < md.nc) {
+        const WbDirW<NV>& d = dw[col];
+        const int bc = md.contact_body[c];
+        if (bc >= d.b0 && bc < d.b0 + d.nbd) {
+          float pc[3];
+          cross3(d.Sd, tr.rc[c], pc);
+          for (int k = 0; k < 3; ++k) { pc[k] += d.Sd[3 + k]; df[k] = pc[k]; }
+          const uint32_t mask = md.contact_dofmask[c];
+          for (int i = 0; i < md.nv; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            float dJ[3];
+            if ((d.moves >> i) & 1u) cross3(d.Sd, J + i * NF + 3 * c, dJ);
+            else cross3(tr.S[i], pc, dJ);
+            for (int k = 0; k < 3; ++k) hc[k] = fmaf(dJ[k], wvz[i], hc[k]);
+          }
+        }
+      }
+      for (int k = 0; k < 3; ++k) {
+        fold[(3 * NV + 3 * c + k) * FW + col] = hc[k];
+        fold[(3 * NV + NF + 3 * c + k) * FW + col] = df[k];
+      }
+    }
+  }
+}
+
 }  // namespace mpxb

@@ -99,11 +99,18 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
   wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
   wb_tree_items(md, tr, 0, 1, nosync);
+  constexpr int NF = 3 * NC, FW = 2 * NV + 1;
+  static WbDirW<NV> dw[NV + 1];
+  static float fold[(3 * NV + 2 * NF) * FW];
+  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, 0, 1, nosync);
   std::vector<float> col(n);
   for (int d = 0; d < nq + nv + m; ++d) {
-    float t1[NV] = {0}, t2[NV] = {0}, e[NV] = {0}, h[3 * NC] = {0}, dfeet[3 * NC] = {0};
+    float t1[NV] = {0};
     const int is_u = d >= nq + nv;
-    if (!is_u) wb_tree_fold(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, d, t1, t2, e, h, dfeet);
+    const int cc = is_u ? 0 : d;
+    if (!is_u) for (int i = 0; i < NV; ++i) t1[i] = fold[i * FW + d];
+    const WbStrided t2{fold + NV * FW + cc, FW}, e{fold + 2 * NV * FW + cc, FW}, h{fold + 3 * NV * FW + cc, FW},
+        dfeet{fold + (3 * NV + NF) * FW + cc, FW};
     float* cp = col.data();
     if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
