@@ -43,6 +43,9 @@ struct TrialOut {
   // launched, the one whose condition fails exits at once.  sel: 0 run, 1 run iff *need_count <= thr, 2 iff > thr
   int32_t* need_count;
   int sel, thr;
+  // a single-point pass behind alpha = 1 (ia0 > 0, nia == 1) clears need[e] when its point is accepted, so that the
+  // remaining points are only evaluated for the environments that reject it as well
+  int update_need;
 };
 
 #if defined(__CUDACC__)
@@ -101,7 +104,20 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
     o.ls_phi[e * NALPHA + ia] = phi;
     if (o.merit) o.ls_vc[e * NALPHA + ia] = vc;
   }
-  if (ia != 0) return;
+  if (ia != 0) {
+    if (o.update_need && o.need && lane == 0) {
+      bool ok;
+      if (o.merit) {
+        float rho, mk, ms;
+        merit_terms(o.theta_k[e], o.phi_k[e], o.vc_k[e], o.dv2[e], o.dvc[e], o.slope[e], &rho, &mk, &ms);
+        ok = !merit_rejected(theta, phi, vc, rho, mk, ms, exp2f(-float(ia)));
+      } else {
+        ok = filter_accept(theta, phi, o.theta_k[e], o.phi_k[e], o.slope[e], exp2f(-float(ia)));
+      }
+      if (ok) o.need[e] = 0;
+    }
+    return;
+  }
   const int N = io.N;
   const size_t nx = size_t(N + 1) * n;
   const float* c = o.c + size_t(e) * nx;

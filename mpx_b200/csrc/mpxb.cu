@@ -186,7 +186,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi, ws + L.c, ws + L.cost, ws + L.slope,
                 ws + L.theta_k, ws + L.phi_k, need, 0, NALPHA, mdl->merit_line_search, ws + L.dV, ws + L.ls_vc,
                 ws + L.vc_k, ws + L.dv2, ws + L.dvc, ws + L.th_part, ws + L.ph_part, ws + L.vc_part,
-                reinterpret_cast<int32_t*>(ws + L.need_count), 0, 0};
+                reinterpret_cast<int32_t*>(ws + L.need_count), 0, 0, 0};
     if (!mdl->eager_line_search) cudaMemsetAsync(to.need_count, 0, sizeof(int32_t), st);
     mpxb_profile* pf = (it == max_iter - 1 && mdl->prof && mdl->prof->calls < mdl->prof->max_calls) ? mdl->prof : nullptr;
     cudaEvent_t* pev = pf ? pf->ev + 5 * pf->calls : nullptr;
@@ -213,9 +213,13 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     // K3: the 11 trial points.  Lazy (default): alpha = 1 first; the ten smaller steps only for the environments
     // whose alpha = 1 point the filter rejects -- the first accepted point is all the reference keeps
     // (optimizers.py:568-572), so X, U, V and alpha_index are unchanged.
-    const int npass = mdl->eager_line_search ? 1 : 2;
+    // Robots whose batches reject alpha = 1 often (H1: ~30 % of the environments) get alpha = 1/2 as a pass of its own,
+    // so the last nine points are evaluated only where both were rejected.
+    const bool three = !mdl->eager_line_search && d.kind != MPXB_KIND_SRBD && d.nv > 18 && E >= 256;
+    const int npass = mdl->eager_line_search ? 1 : (three ? 3 : 2);
     for (int pass = 0; pass < npass; ++pass) {
       if (mdl->eager_line_search) { to.ia0 = 0; to.nia = NALPHA; to.need = nullptr; to.need_count = nullptr; }
+      else if (three) { to.ia0 = pass; to.nia = pass < 2 ? 1 : NALPHA - 2; to.update_need = (pass == 1); }
       else { to.ia0 = pass; to.nia = pass == 0 ? 1 : NALPHA - 1; }
       if (d.kind == MPXB_KIND_SRBD) {
         const int wpb = 4;

@@ -93,6 +93,8 @@ class MpcSolver:
         # wb_class_trial in csrc/wb_kernels.cuh)
         if self.eager_line_search:
             trial = 1
+        elif self.desc.kind != 0 and self.desc.nv > 18 and self.n_env >= 256:
+            trial = 3   # alpha = 1, alpha = 1/2, the rest (warp form; see mpxb_mpc_step)
         elif self.desc.kind != 0 and (self.desc.nv <= 18 or self.n_env * (self.N + 1) <= 148 * 8):
             trial = 2 + 3
         else:
