@@ -97,3 +97,37 @@ def test_batch_independence_and_lazy_equals_eager(full):
     hist = torch.bincount(s_full.alpha_index.long(), minlength=11).tolist()
     print("alpha index histogram:", hist)
     assert sum(hist) == E_FULL
+
+
+def test_three_pass_line_search_equals_eager_h1():
+    """Large H1 / Talos batches run the lazy search in three passes (alpha = 1, alpha = 1/2, the rest; mpxb_mpc_step):
+    on a batch whose environments need different step sizes the result must equal the eager evaluation bitwise."""
+    import importlib
+    import os
+    from mpx_b200.primal_dual_ilqr.optimizers import MpcSolver
+    cfg_h1 = importlib.import_module("mpx_b200.config.config_h1")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h1_warm.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture missing")
+    g = np.load(path)
+    E = 256
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda().contiguous()
+    rep = lambda a: T(np.repeat(np.asarray(a)[:1], E, axis=0))
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    # per-environment perturbation of the warm start, growing with the env index: from "alpha = 1 accepted" to rejected
+    scale = torch.linspace(0.0, 0.3, E, device="cuda")[:, None, None]
+    X0 = rep(g["X0"]); U0 = rep(g["U0"]); V0 = rep(g["V0"])
+    X0 = X0 + scale * torch.randn(X0.shape, device="cuda", generator=gen)
+    U0 = U0 + 10.0 * scale * torch.randn(U0.shape, device="cuda", generator=gen)
+    out = {}
+    for eager in (True, False):
+        s = MpcSolver(cfg_h1, E, limited_memory=True, eager_line_search=eager)
+        X, U, V = s.solve(rep(g["reference"]), rep(g["parameter"]), T(cfg_h1.W), rep(g["x0"]), X0, U0, V0)
+        torch.cuda.synchronize()
+        out[eager] = (s.alpha_index.clone(), X, U, V)
+    hist = torch.bincount(out[True][0].long(), minlength=11).tolist()
+    print("alpha index histogram (H1 x256):", hist)
+    assert sum(1 for h in hist if h > 0) >= 3, hist  # the batch really exercises all three passes
+    assert torch.equal(out[True][0], out[False][0])
+    for a, b in zip(out[True][1:], out[False][1:]):
+        assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
