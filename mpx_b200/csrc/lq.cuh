@@ -53,7 +53,7 @@ template <int n, int m> __host__ __device__ inline LqRtLayout lq_rt_layout(int L
   o.oP = 0;
   o.oA = LN * LN;                 // [LN][LZ]
   o.oT = o.oA + LN * LZ;          // T1 [LN][LZ], then Q_t [n][n]
-  const int szT = (LN * LZ > lq_pad(n * n)) ? LN * LZ : lq_pad(n * n);
+  const int szT = (LN * LZ > lq_pad(n * n + 3)) ? LN * LZ : lq_pad(n * n + 3);  // + 3: cp_async_flat slack
   o.oB = o.oT + szT;              // [LN][LM]
   o.oPB = o.oB + LN * LM;         // [LN][LM]
   o.oH = o.oPB + LN * LM;         // [LM][LN]
@@ -70,7 +70,7 @@ template <int n, int m> __host__ __device__ constexpr int lq_rt_min_blocks() {
   constexpr int LN = lq_pad(n), LM = lq_pad(m);
   constexpr int nzc = (n == 61 && m == 12) ? 37 : (n == 75 && m == 19) ? 51 : (n == 81 && m == 46) ? 57 : n;
   constexpr int LZ = lq_pad(nzc);
-  constexpr int szT = (LN * LZ > lq_pad(n * n)) ? LN * LZ : lq_pad(n * n);
+  constexpr int szT = (LN * LZ > lq_pad(n * n + 3)) ? LN * LZ : lq_pad(n * n + 3);
   constexpr int total = LN * LN + LN * LZ + szT + 2 * LN * LM + 2 * LM * LN + LM * LM + 5 * LN + 4 * LM + 8 + lq_pad(m * m);
   constexpr int b = 232448 / (total * 4 + 1024);
   return b < 1 ? 1 : (b > 4 ? 4 : b);
@@ -133,6 +133,26 @@ __device__ __forceinline__ void load_padded(float* __restrict__ dst, int ld, int
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
   const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+// Asynchronous copy of `count` contiguous floats whose global address is only 4-byte aligned: the destination is
+// shifted by the source's offset inside its 16-byte line (0..3 floats; `dst_base` is 16-byte aligned and has 3 floats
+// of slack), so everything but a head / tail of at most 3 floats moves as 16-byte cp.async.  Returns the shifted
+// destination.
+__device__ __forceinline__ float* cp_async_flat(float* dst_base, const float* src, int count, int tid, int nthreads) {
+  const int sh = int((reinterpret_cast<unsigned long long>(src) >> 2) & 3ull);
+  float* dst = dst_base + sh;
+  int head = (4 - sh) & 3;
+  if (head > count) head = count;
+  if (tid < head) cp_async4(dst + tid, src + tid);
+  const int nvec = (count - head) >> 2;
+  for (int v = tid; v < nvec; v += nthreads) cp_async16(dst + head + 4 * v, src + head + 4 * v);
+  const int done = head + 4 * nvec;
+  if (tid < count - done) cp_async4(dst + done + tid, src + done + tid);
+  return dst;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -554,7 +574,7 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
     }
     __syncthreads();
     // prefetch: Q_t over T1, A_{t-1} / B_{t-1} over A_t / B_t
-    for (int i = tid; i < n * n; i += NT) cp_async4(sT + i, gQ + size_t(t) * n * n + i);  // unpadded [n][n]
+    const float* sQ = cp_async_flat(sT, gQ + size_t(t) * n * n, n * n, tid, NT);  // unpadded [n][n], 16-byte copies
     if (t > 0) {
       cp_async_matrix(sA, LZ, gA + size_t(t - 1) * n * n, n, n, acols, tid, NT);
       cp_async_matrix(sB, LM, gB + size_t(t - 1) * n * m, n, m, m, tid, NT);
@@ -664,8 +684,8 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
       int j = i + d;
       if (j >= LN) j -= LN;
       if ((2 * d == LN && i >= LN / 2) || i >= n || j >= n) continue;
-      const float zij = sT[i * n + j] + sP[i * LN + j];
-      const float zji = sT[j * n + i] + sP[j * LN + i];
+      const float zij = sQ[i * n + j] + sP[i * LN + j];
+      const float zji = sQ[j * n + i] + sP[j * LN + i];
       const float s = 0.5f * (zij + zji);
       sP[i * LN + j] = s;
       sP[j * LN + i] = s;
