@@ -168,11 +168,11 @@ __device__ __forceinline__ void wb_cost_rowsums(const WbModel& md, const ModelIO
 template <int NV, int NC>
 __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
                                                float* sgrad, const float* satv, const float* sG,
-                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT) {
+                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT, const float* Wov = nullptr) {
   constexpr int NJ = NV - 6, NF = 3 * NC;
   const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
   const bool term = (t == N);
-  const float* W = io.W + size_t(e) * io.w_stride;
+  const float* W = Wov ? Wov : io.W + size_t(e) * io.w_stride;
   const int nw = md.nw;
   const float* contact = ref + 13 + nj + nf;
   const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
@@ -232,11 +232,11 @@ __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO&
 template <int NV, int NC>
 __device__ __forceinline__ void wb_gn_blocks(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
                                              const float* sx, const float* su, const float* sG,
-                                             const WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT) {
+                                             const WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT, const float* Wov = nullptr) {
   constexpr int NJ = NV - 6, NF = 3 * NC;
   const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
   const bool term = (t == N);
-  const float* W = io.W + size_t(e) * io.w_stride;
+  const float* W = Wov ? Wov : io.W + size_t(e) * io.w_stride;
   const int nw = md.nw;
   const float* contact = ref + 13 + nj + nf;
   const int ua0 = 12 + 2 * nj + nf;  // residual row of u[0]
@@ -463,16 +463,24 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 #endif
 template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
+  static constexpr int NW = 12 + 3 * NJ + 2 * NF;
   WbKnot<NV, NC> k;
-  WbTree<NB, NV, NC, NI> tr;
   WbCostSmem<NV, NC> cs;
   float sref[13 + NJ + 7 * NC];
+  float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
+  // tr | fold | dw are dead once the columns of [A | B] are out: the weight matrix W is staged over them for the
+  // Gauss-Newton / cost stage (its reads would otherwise go to L2: 216 KB of shared memory leave ~40 KB of L1)
+  alignas(16) WbTree<NB, NV, NC, NI> tr;
   // folded tangents t1 | t2 | e | h | dfeet of every x-direction ([row][direction], wb_tree_fold_coop) + direction frames
   static constexpr int FW = 2 * NV + 1;
   float fold[(3 * NV + 2 * NF) * FW];
   WbDirW<NV> dw[NV + 1];
-  float sx[NX], su[NU], svn[NX], sgrad[NX + NU], satv[NX + NU], sG[12];
 };
+
+__device__ __forceinline__ void wb_cp_async16(float* dst, const float* src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
 
 template <int NB, int NV, int NC, int NI, int NT>
 __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
@@ -565,11 +573,24 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       A[i * n + j] = 0.f;
     }
   }
-  wb_gn_blocks<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
   if (t == 0)
     for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
-  __syncthreads();
-  wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT);
+  // stage W over the dead tree / fold arrays (16-byte cp.async when it is 16-byte aligned and fits)
+  const float* Wg = io.W + size_t(e) * io.w_stride;
+  const float* Wuse = nullptr;
+  const int nww = md.nw * md.nw;
+  __syncthreads();  // every worker is done with tr / fold / dw
+  if ((reinterpret_cast<unsigned long long>(Wg) & 15ull) == 0 && (nww & 3) == 0 &&
+      size_t(nww) * sizeof(float) <= sizeof(sm.tr) + sizeof(sm.fold) + sizeof(sm.dw)) {
+    float* sW = reinterpret_cast<float*>(&sm.tr);
+    for (int v = tid; v < nww / 4; v += NT) wb_cp_async16(sW + 4 * v, Wg + 4 * v);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    Wuse = sW;
+  }
+  wb_gn_blocks<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT, Wuse);
+  wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, Wuse);
 }
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
