@@ -169,6 +169,92 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------- latency leg
+def _pct(a, q):
+    return float(np.percentile(np.asarray(a, dtype=np.float64), q))
+
+
+def latency_leg(dev, ticks=1000, warm=20):
+    """p50 / p99 single-solve latency (BASELINE.json metric, second half): E = 1, `ticks` consecutive
+    closed-loop ticks through the public wrapper call with HOST buffers, host wall clock around
+    H2D + launch + D2H + sync, and CUDA-event time of the same region.
+
+    * Aliengo SRBD (BASELINE configs[0], north-star target p50 < 1 ms): mpc_wrapper_srbd.BatchedMPCControllerWrapper
+      `.run` (one launch per kernel) and `.graph_run` (the same tick replayed from a CUDA graph);
+    * Aliengo whole-body (configs[1]): MPCControllerWrapper.run, numpy in / numpy out like the reference."""
+    import torch
+    from mpx_b200.utils.mpc_wrapper import MPCControllerWrapper
+    from mpx_b200.utils.mpc_wrapper_srbd import BatchedMPCControllerWrapper as SrbdWrapper
+    out = {"ticks": ticks, "timing": "host wall clock around H2D + wrapper call + D2H + stream sync; device = CUDA events around the same region"}
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- Aliengo SRBD, E = 1
+    cfg = importlib.import_module("mpx_b200.config.config_srbd")
+    nc = cfg.n_contact
+    st = synthetic_states(cfg, 1, seed=123)
+    yaw = float(st["yaw"][0])
+    Ry = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    base = np.array([st["qpos"][0, 0], st["qpos"][0, 1], 0.0])
+    feet0 = (base[None] + np.asarray(cfg.p_legs0).reshape(nc, 3) @ Ry.T).reshape(1, -1).astype(np.float32)
+    x00 = np.concatenate([st["qpos"][:, :7], st["qvel"][:, :6]], 1).astype(np.float32)
+    for mode in ("eager", "graph"):
+        wrap = SrbdWrapper(cfg, 1, device=dev)
+        shift = wrap.shift
+        wrap.contact_time.copy_(torch.as_tensor(st["timer"]))
+        wrap.liftoff.copy_(torch.as_tensor(feet0))
+        x0_h, cmd_h = torch.as_tensor(x00).pin_memory(), torch.as_tensor(st["cmd"]).pin_memory()
+        feet_h, con_h = torch.as_tensor(feet0).pin_memory(), torch.ones(1, nc).pin_memory()
+        grf_h = torch.empty(1, 3 * nc).pin_memory()
+        x0_d, cmd_d, feet_d, con_d = (torch.empty_like(t, device=dev) for t in (x0_h, cmd_h, feet_h, con_h))
+        call = wrap.run if mode == "eager" else wrap.graph_run
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall, devt = [], []
+        for i in range(warm + ticks):
+            t0 = time.perf_counter()
+            e0.record()
+            x0_d.copy_(x0_h, non_blocking=True); cmd_d.copy_(cmd_h, non_blocking=True)
+            feet_d.copy_(feet_h, non_blocking=True); con_d.copy_(con_h, non_blocking=True)
+            call(x0_d, cmd_d, feet_d, con_d)
+            grf_h.copy_(wrap.grf, non_blocking=True)
+            e1.record()
+            stream.synchronize()
+            t1 = time.perf_counter()
+            if i >= warm:
+                wall.append((t1 - t0) * 1e3); devt.append(e0.elapsed_time(e1))
+            # simulator stand-in (not timed): the next measured state is the model's own prediction
+            x0_h.copy_(wrap.X[:, shift, :]); feet_h.copy_(wrap.parameter[:, 0, 4:])
+        ok = bool(torch.isfinite(wrap.X).all().item())
+        out["srbd_" + mode] = {"workload": "Aliengo SRBD MPC, single instance (mpc_wrapper_srbd %s)" % ("run" if mode == "eager" else "graph_run, CUDA-graph replay"),
+                               "p50_ms": _pct(wall, 50), "p99_ms": _pct(wall, 99), "p50_device_ms": _pct(devt, 50),
+                               "p99_device_ms": _pct(devt, 99), "finite": ok}
+        del wrap
+
+    # ---- Aliengo whole-body, E = 1, numpy API
+    cfg = importlib.import_module("mpx_b200.config.config_aliengo")
+    nj, ncw = cfg.n_joints, cfg.n_contact
+    st = synthetic_states(cfg, 1, seed=124)
+    wrap = MPCControllerWrapper(cfg, limited_memory=False, device=dev)
+    qpos, qvel = st["qpos"][0].astype(np.float64), st["qvel"][0].astype(np.float64)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        wrap.reset(qpos, qvel)
+    cmd, contact = st["cmd"][0].astype(np.float64), np.ones(ncw)
+    wall = []
+    for i in range(warm + ticks):
+        t0 = time.perf_counter()
+        tau, q, dq = wrap.run(qpos, qvel, cmd, contact)
+        t1 = time.perf_counter()
+        if i >= warm:
+            wall.append((t1 - t0) * 1e3)
+        x1 = wrap.X[0, wrap.shift].cpu().numpy().astype(np.float64)
+        qpos, qvel = x1[:7 + nj], x1[7 + nj:13 + 2 * nj]
+    out["aliengo_wb"] = {"workload": "Aliengo whole-body MPC, single instance (MPCControllerWrapper.run, numpy in / numpy out)",
+                         "p50_ms": _pct(wall, 50), "p99_ms": _pct(wall, 99), "finite": bool(np.isfinite(tau).all())}
+    best = min(out["srbd_eager"], out["srbd_graph"], key=lambda d: d["p50_ms"])
+    out["p50_ms"], out["p99_ms"], out["workload"] = best["p50_ms"], best["p99_ms"], best["workload"]
+    return out
+
+
 # --------------------------------------------------------------------------------------------- native arm
 def run_native(args):
     import ctypes as C
@@ -190,6 +276,11 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     robot, desc = WORKLOADS[args.workload]
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
+    if args.horizon and args.horizon != cfg.N:
+        # horizon sweep (BASELINE configs[3]): the same config with N replaced; every kernel takes N at run time
+        from types import SimpleNamespace
+        cfg = SimpleNamespace(**{k: getattr(cfg, k) for k in dir(cfg) if not k.startswith("__")})
+        cfg.N = int(args.horizon)
     E, K, Wm = args.envs, args.steps, args.warmup
     srbd = robot == "srbd"
     lib = _lib.lib()
@@ -324,6 +415,39 @@ def run_native(args):
                "ms_per_step": t_e2e / K,
                "api": "BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
 
+    else:
+        x0_h = torch.empty(E, n, dtype=torch.float32).pin_memory()
+        x0_h.copy_(x_init.cpu())
+        cmd_h = torch.as_tensor(st["cmd"]).pin_memory()
+        feet_h = tape[0][1][:, 0, 4:].cpu().pin_memory()
+        con_h = torch.ones(E, nc).pin_memory()
+        grf_h = torch.empty(E, 3 * nc, dtype=torch.float32).pin_memory()
+        wrap.reset(verbose=False)
+        wrap.contact_time = T(st["timer"])
+        wrap.liftoff = feet_h.to(dev)
+
+        def tick_srbd():
+            wrap.run(x0_h.to(dev, non_blocking=True), cmd_h.to(dev, non_blocking=True), feet_h.to(dev, non_blocking=True),
+                     con_h.to(dev, non_blocking=True))
+            grf_h.copy_(wrap.grf, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()     # the caller reads the GRFs
+            x0_h.copy_(wrap.X[:, shift, :], non_blocking=True)   # simulator stand-in (not counted)
+            feet_h.copy_(wrap.parameter[:, 0, 4:], non_blocking=True)
+        for _ in range(max(Wm, 3)):
+            tick_srbd()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            tick_srbd()
+        e1.record()
+        barrier()
+        t_e2e = max_over_ranks(e0.elapsed_time(e1), device=dev)
+        e2e = {"value": E * world * K / (t_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(E * (n + 7 + 3 * nc + nc) * 4), "d2h_bytes_per_step": int(E * 3 * nc * 4),
+               "ms_per_step": t_e2e / K,
+               "api": "mpc_wrapper_srbd.BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
+
     # final gather of the controls (the only collective; north_star), outside the timed solve path
     if world > 1:
         gather_controls(U[:, 0, :nj].contiguous(), n_env_total=E * world, dst=0)
@@ -360,6 +484,9 @@ def run_native(args):
                                    "note": "SURVEY.md 8(d): F_lqr x solves/s / FP32 peak over the whole tick (linearise + LQ + line search + shift)"},
                     "kernel_ms": kernel_ms, "dominant_kernel": dom,
                     "share_of_step": {k: v / (ms_total / K) for k, v in kernel_ms.items()}}
+        latency = None
+        if world == 1 and not args.no_latency:
+            latency = latency_leg(dev, ticks=args.latency_ticks)
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -374,7 +501,7 @@ def run_native(args):
                            "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
                            "parallelism": f"env-sharded x{world}, no collective on the solve path"},
                 "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "clocks": clocks, "nonfinite_envs": nonfinite_envs,
+                "latency": latency, "clocks": clocks, "nonfinite_envs": nonfinite_envs,
                 "alpha_index_hist_last_step": alpha_hist}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -390,7 +517,10 @@ def main():
     ap.add_argument("--workload", default="go2_wb", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
     ap.add_argument("--scan", action="store_true", help="associative-scan LQ (limited_memory=False)")
+    ap.add_argument("--horizon", type=int, default=0, help="override config.N (horizon sweep, e.g. Talos 25/50/100/200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the E = 1 p50 / p99 latency leg")
+    ap.add_argument("--latency-ticks", type=int, default=1000)
     ap.add_argument("--prewarm-s", type=float, default=2.0, help="seconds of untimed device pre-warm before the warm-up steps")
     ap.add_argument("--ref-max-steps", type=int, default=4)
     args = ap.parse_args()

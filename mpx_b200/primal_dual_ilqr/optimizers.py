@@ -192,9 +192,9 @@ class MpcSolver:
         wb = self.desc.kind != _lib.KIND_SRBD
         tau = q = dq = None
         if wb and want_cmd:
-            tau = torch.empty(E, nj, dtype=torch.float32, device=self.device)
-            q = torch.empty_like(tau)
-            dq = torch.empty_like(tau)
+            # one [3, E, nj] buffer so that a caller that wants all three on the host pays a single D2H copy
+            self.cmd_pack = torch.empty(3, E, nj, dtype=torch.float32, device=self.device)
+            tau, q, dq = self.cmd_pack[0], self.cmd_pack[1], self.cmd_pack[2]
         p = lambda t: t.data_ptr() if t is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.mpxb_shift_extract(self.handle, stream, E, int(shift), p(X), p(U), p(V), p(x0), p(u_ref),

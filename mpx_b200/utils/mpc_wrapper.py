@@ -219,8 +219,9 @@ class MPCControllerWrapper(_Base):
         X, U, V = self._solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
         tau, q, dq = self._solver.shift_extract(X, U, V, x0, self.u_ref, self.X0, self.U0, self.V0, self.shift)
         self.X, self.U, self.V = X, U, V
-        tau = np.clip(tau[0].cpu().numpy(), cfg.min_torque, cfg.max_torque)
-        return tau, q[0].cpu().numpy(), dq[0].cpu().numpy()
+        cmd = self._solver.cmd_pack[:, 0, :].cpu().numpy()     # (tau, q, dq): the one blocking D2H read of the tick
+        tau = np.clip(cmd[0], cfg.min_torque, cfg.max_torque)
+        return tau, cmd[1], cmd[2]
 
     def reset(self, qpos, qvel):
         """reference mpc_wrapper.py:366-385."""

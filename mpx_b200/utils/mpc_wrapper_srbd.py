@@ -76,6 +76,33 @@ class BatchedMPCControllerWrapper:
         self.X, self.U, self.V = X, U, V
         return 0
 
+    def graph_run(self, x0, input, foot_op, contact):
+        """``run`` replayed from a CUDA graph (one launch per tick instead of one per kernel): the first call captures
+        reference generator + solve + shift on static input buffers, later calls copy the arguments into them and replay.
+        Same results and the same state updates as ``run``; ``reset`` drops the graph."""
+        args = tuple(self._as(t).contiguous() for t in (x0, input, foot_op, contact))
+        if getattr(self, "_graph", None) is None:
+            self._graph_in = tuple(t.clone() for t in args)
+            state = (self.contact_time, self.liftoff, self.batch_X0, self.batch_U0, self.batch_V0)
+            saved = tuple(t.clone() for t in state)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.run(*self._graph_in)          # warm-up outside the capture (module load, kernel attributes)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self.run(*self._graph_in)
+                for t, s in zip(state, saved):     # neither the warm-up nor the capture may advance the controller
+                    t.copy_(s)
+            cur.wait_stream(side)
+            self._graph = graph
+        else:
+            for dst, src in zip(self._graph_in, args):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return 0
+
     def _as(self, t):
         if not torch.is_tensor(t):
             t = torch.as_tensor(np.asarray(t), dtype=torch.float32)
@@ -132,6 +159,7 @@ class BatchedMPCControllerWrapper:
     def reset(self, verbose=True):
         """mpc_wrapper_srbd.py:162-174."""
         cfg, E = self.config, self.n_env
+        self._graph = None
         self.contact_time = self._T(cfg.timer_t).repeat(E, 1)
         self.liftoff = torch.zeros(E, 3 * cfg.n_contact, device=self.device)
         self.contact = torch.ones(E, cfg.n_contact, device=self.device)
