@@ -289,6 +289,8 @@ def run_native(args):
     N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
     lm = not args.scan
     if args.scan:
+        if args.scan_schedule:
+            os.environ["MPXB_SCAN_SCHEDULE"] = args.scan_schedule
         os.environ["MPXB_LQ"] = "scan"  # bind the associative-scan kernel literally (wrappers default to the sequential one)
 
     if srbd:
@@ -497,7 +499,7 @@ def run_native(args):
                 "warmup": max(Wm, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "robot": robot, "envs_per_gpu": E, "n": n, "m": m, "horizon": N,
-                           "lq": "sequential" if lm else "scan", "sqp_iterations_per_step": 1,
+                           "lq": "sequential" if lm else ("scan" + ("-" + args.scan_schedule if args.scan_schedule else "")), "sqp_iterations_per_step": 1,
                            "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
                            "parallelism": f"env-sharded x{world}, no collective on the solve path"},
                 "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -517,6 +519,8 @@ def main():
     ap.add_argument("--workload", default="go2_wb", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
     ap.add_argument("--scan", action="store_true", help="associative-scan LQ (limited_memory=False)")
+    ap.add_argument("--scan-schedule", default="", choices=["", "serial", "parallel"],
+                    help="force the schedule of the associative scan (default: parallel over the horizon for E <= 64)")
     ap.add_argument("--horizon", type=int, default=0, help="override config.N (horizon sweep, e.g. Talos 25/50/100/200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the E = 1 p50 / p99 latency leg")

@@ -42,7 +42,11 @@ enum {
 /* LQ sub-problem solver == the reference's `limited_memory` static argument (optimizers.py:175-180) */
 enum {
   MPXB_LQ_SEQUENTIAL = 0, /* tvlqr + rollout          (primal_tvlqr.py:103-144, 478-498)  limited_memory=True  */
-  MPXB_LQ_SCAN = 1        /* tvlqr_gpu + rollout_gpu  (primal_tvlqr.py:337-475, 523-549)  limited_memory=False */
+  MPXB_LQ_SCAN = 1,       /* tvlqr_gpu + rollout_gpu  (primal_tvlqr.py:337-475, 523-549)  limited_memory=False:
+                             the associative scan, scheduled in parallel over the horizon (one CTA per knot,
+                             ceil(log2(N+1)) levels) for small batches and serially per environment for large ones */
+  MPXB_LQ_SCAN_SERIAL = 2,   /* force the one-CTA-per-environment schedule of the same scan */
+  MPXB_LQ_SCAN_PARALLEL = 3  /* force the parallel-in-time schedule (E <= 64) */
 };
 
 enum {

@@ -17,6 +17,7 @@
 #include "srbd_kernels.cuh"
 #include "wb_launch.h"
 #include "lq_scan.cuh"
+#include "lq_pscan.cuh"
 #include "refgen.cuh"
 
 using namespace mpxb;
@@ -144,9 +145,27 @@ void mpxb_model_destroy(mpxb_model* m) {
   delete m;
 }
 
+// MPXB_LQ_SCAN picks the schedule of the associative scan by batch size: the parallel (Hillis-Steele, one CTA per
+// knot) schedule up to PSCAN_MAX_ENVS environments, the serial one-CTA-per-environment schedule above;
+// MPXB_LQ_SCAN_SERIAL / MPXB_LQ_SCAN_PARALLEL force one (the parallel one only where its scratch is provided for).
+static bool lq_mode_valid(int lq_mode, int E) {
+  if (lq_mode == MPXB_LQ_SEQUENTIAL || lq_mode == MPXB_LQ_SCAN || lq_mode == MPXB_LQ_SCAN_SERIAL) return true;
+  return lq_mode == MPXB_LQ_SCAN_PARALLEL && pscan_applies(E);
+}
+static size_t lq_scan_ws_floats(int lq_mode, int E, int N, int n) {
+  const bool par = (lq_mode == MPXB_LQ_SCAN || lq_mode == MPXB_LQ_SCAN_PARALLEL) && pscan_applies(E);
+  return par ? lq_pscan_floats(E, N, n) : 0;
+}
+static int dispatch_lq(int lq_mode, int n, int m, const LqArgs& la, float* scan_ws, cudaStream_t st) {
+  if (lq_mode == MPXB_LQ_SEQUENTIAL) return dispatch_lq_seq(n, m, la, st);
+  if (lq_mode == MPXB_LQ_SCAN_PARALLEL || (lq_mode == MPXB_LQ_SCAN && pscan_applies(la.E)))
+    return dispatch_lq_pscan(n, m, la, scan_ws, st);
+  return dispatch_lq_scan(n, m, la, scan_ws, st);
+}
+
 static WsLayout layout_of(const mpxb_model* mdl, int E, int lq_mode) {
   const mpxb_model_desc& d = mdl->desc;
-  size_t scan = (lq_mode == MPXB_LQ_SCAN) ? lq_scan_floats(E, d.N, d.n, d.m) : 0;
+  size_t scan = lq_scan_ws_floats(lq_mode, E, d.N, d.n);
   return make_layout(E, d.N, d.n, d.m, scan);
 }
 
@@ -162,7 +181,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
   if (!mdl || !reference || !parameter || !W || !x0 || !X_in || !U_in || !V_in || !X || !U || !V || !workspace)
     return MPXB_EINVAL;
   if (E <= 0 || max_iter <= 0) return MPXB_EINVAL;
-  if (lq_mode != MPXB_LQ_SEQUENTIAL && lq_mode != MPXB_LQ_SCAN) return MPXB_EINVAL;
+  if (!lq_mode_valid(lq_mode, E)) return MPXB_EINVAL;
   if (X == X_in || U == U_in || V == V_in) return MPXB_EINVAL;
   const mpxb_model_desc& d = mdl->desc;
   const WsLayout L = layout_of(mdl, E, lq_mode);
@@ -206,8 +225,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
               ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done,
               // whole-body models: the foot / GRF tail of the state never enters f, so those columns of A are zero
               d.kind == MPXB_KIND_SRBD ? 0 : 13 + 2 * d.n_joints};
-    int rc = (lq_mode == MPXB_LQ_SEQUENTIAL) ? dispatch_lq_seq(n, m, la, st)
-                                             : dispatch_lq_scan(n, m, la, ws + L.scan, st);
+    int rc = dispatch_lq(lq_mode, n, m, la, ws + L.scan, st);
     if (rc != MPXB_OK) return rc;
     if (pev) cudaEventRecord(pev[2], st);
     // K3: the 11 trial points.  Lazy (default): alpha = 1 first; the ten smaller steps only for the environments
@@ -370,12 +388,15 @@ int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const floa
   if (!Q || !q || !R || !r || !M || !A || !B || !c || !K || !k || !P || !p || !dX || !dU || !dV || !slope) return MPXB_EINVAL;
   LqArgs la{E, N, A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, slope, nullptr, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (lq_mode == MPXB_LQ_SEQUENTIAL) return dispatch_lq_seq(n, m, la, st);
-  if (!scan_ws) return MPXB_EINVAL;
-  return dispatch_lq_scan(n, m, la, static_cast<float*>(scan_ws), st);
+  if (E <= 0 || N <= 0 || !lq_mode_valid(lq_mode, E)) return MPXB_EINVAL;
+  if (lq_mode != MPXB_LQ_SEQUENTIAL && !scan_ws) return MPXB_EINVAL;
+  return dispatch_lq(lq_mode, n, m, la, static_cast<float*>(scan_ws), st);
 }
 
-size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m) { return lq_scan_floats(E, N, n, m) * sizeof(float); }
+size_t mpxb_tvlqr_scan_bytes(int E, int N, int n, int m) {
+  (void)m;
+  return lq_scan_ws_floats(MPXB_LQ_SCAN, E, N, n) * sizeof(float);
+}
 
 __global__ void fp32_peak_kernel(float* out, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,

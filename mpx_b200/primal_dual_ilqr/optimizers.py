@@ -54,13 +54,20 @@ class MpcSolver:
     """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
 
     def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None,
-                 eager_line_search=False, line_search="filter"):
+                 eager_line_search=False, line_search="filter", lq_mode=None):
         if not torch.cuda.is_available():
             raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.n_env = int(n_env)
-        self.lq_mode = _lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN
+        self.lq_mode = (_lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN) if lq_mode is None else int(lq_mode)
+        if lq_mode is None and not limited_memory:
+            # MPXB_SCAN_SCHEDULE=serial|parallel forces a schedule of the associative scan (benchmarks / profiling)
+            import os
+            forced = {"serial": _lib.LQ_SCAN_SERIAL, "parallel": _lib.LQ_SCAN_PARALLEL}.get(
+                os.environ.get("MPXB_SCAN_SCHEDULE", "").lower())
+            if forced is not None:
+                self.lq_mode = forced
         self.max_iter = int(max_iter)
         self.desc = _lib.make_desc(config, robot_model)
         self.N, self.n, self.m = self.desc.N, self.desc.n, self.desc.m
@@ -99,7 +106,10 @@ class MpcSolver:
             trial = 2 + 3
         else:
             trial = 2
-        self.launches_per_call = (3 + trial) * self.max_iter
+        # the parallel-in-time scan is elements + ceil(log2(N+1)) levels + gains + rollout; the other LQ kernels are one launch
+        parallel_scan = self.lq_mode == _lib.LQ_SCAN_PARALLEL or (self.lq_mode == _lib.LQ_SCAN and self.n_env <= 64)
+        lq = 3 + int(self.N).bit_length() if parallel_scan else 1
+        self.launches_per_call = (2 + lq + trial) * self.max_iter
 
     def __del__(self):
         try:
@@ -257,11 +267,13 @@ def mpc(cost, dynamics, hessian_approx, limited_mempory, reference, parameter, W
     return X, U, V
 
 
-def tvlqr_solve(Q, q, R, r, M, A, B, c, limited_memory=True):
+def tvlqr_solve(Q, q, R, r, M, A, B, c, limited_memory=True, lq_mode=None):
     """Batched LQ sub-problem on the GPU: tvlqr+rollout+dual_lqr (limited_memory=True) or the scan forms.
 
     Reference: compute_search_direction's LQ half (optimizers.py:175-182).  All inputs [E, ...] CUDA float32;
     ``c`` is [E, N+1, n] (c[:,0] = rollout start, c[:,1:] = offsets).  Returns K, k, P, p, dX, dU, dV, slope.
+    ``lq_mode`` overrides ``limited_memory`` with one of ``_lib.LQ_*`` (LQ_SCAN_SERIAL / LQ_SCAN_PARALLEL force a
+    schedule of the associative scan; LQ_SCAN picks the parallel-in-time one for E <= 64).
     """
     lib = _lib.lib()
     for t in (Q, q, R, r, M, A, B, c):
@@ -272,9 +284,9 @@ def tvlqr_solve(Q, q, R, r, M, A, B, c, limited_memory=True):
     mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     K, k, P, p = mk(E, N, m, n), mk(E, N, m), mk(E, N + 1, n, n), mk(E, N + 1, n)
     dX, dU, dV, slope = mk(E, N + 1, n), mk(E, N, m), mk(E, N + 1, n), mk(E)
-    mode = _lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN
+    mode = (_lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN) if lq_mode is None else int(lq_mode)
     scan = None
-    if not limited_memory:
+    if mode != _lib.LQ_SEQUENTIAL:
         scan = torch.empty(max(lib.mpxb_tvlqr_scan_bytes(E, N, n, m), 4), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     rc = lib.mpxb_tvlqr(stream, E, N, n, m, mode, Q.data_ptr(), q.data_ptr(), R.data_ptr(), r.data_ptr(),

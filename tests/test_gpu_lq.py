@@ -47,16 +47,36 @@ def test_reference_simple_lqr_problem(limited_memory):
 
 
 @pytest.mark.parametrize("n,m,T", [(4, 1, 50), (8, 2, 30), (13, 12, 25), (61, 12, 25), (75, 19, 25), (81, 46, 25), (81, 46, 60)])
-@pytest.mark.parametrize("limited_memory", [True, False])
-def test_random_lq(n, m, T, limited_memory):
+@pytest.mark.parametrize("lq_mode", [0, 1, 2, 3], ids=["sequential", "scan", "scan_serial", "scan_parallel"])
+def test_random_lq(n, m, T, lq_mode):
+    """Every LQ kernel: sequential Riccati, and the associative scan in both schedules (parallel over the horizon,
+    one CTA per knot and log2 levels; serial, one CTA per environment) -- `scan` picks the parallel one at E = 2."""
     from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
     prob = random_lq(n, m, T, seed=n + T)
-    got = tvlqr_solve(*_to_gpu(prob, 2), limited_memory=limited_memory)
+    got = tvlqr_solve(*_to_gpu(prob, 2), lq_mode=lq_mode)
     # FP32 budget: the float32 oracle's own error against float64 is ~1e-5 on these problems
-    _check(got, _oracle(prob, not limited_memory), 2e-4)
+    _check(got, _oracle(prob, lq_mode != 0), 2e-4)
     # batch entries are independent and identical
     for g in got:
         assert torch.equal(g[0], g[1])
+
+
+def test_parallel_scan_long_horizon_and_odd_lengths():
+    """Hillis-Steele levels with N + 1 not a power of two, and a long horizon (Talos sizes, N = 200)."""
+    from mpx_b200 import _lib
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    for n, m, T in [(8, 2, 1), (8, 2, 2), (8, 2, 7), (13, 12, 33), (81, 46, 200)]:
+        prob = random_lq(n, m, T, seed=3 * n + T)
+        got = tvlqr_solve(*_to_gpu(prob, 1), lq_mode=_lib.LQ_SCAN_PARALLEL)
+        _check(got, _oracle(prob, True), 5e-4 if T > 100 else 2e-4)
+
+
+def test_parallel_scan_rejected_for_large_batches():
+    from mpx_b200 import _lib
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    prob = random_lq(4, 1, 3, seed=1)
+    with pytest.raises(RuntimeError):
+        tvlqr_solve(*_to_gpu(prob, 65), lq_mode=_lib.LQ_SCAN_PARALLEL)
 
 
 def test_unsupported_dims_rejected():
