@@ -33,6 +33,137 @@ constexpr int PSCAN_MAX_ENVS = 64;
 inline bool pscan_applies(int E) { return E <= PSCAN_MAX_ENVS; }
 inline size_t lq_pscan_floats(int E, int N, int n) { return 2 * pscan_buf_floats(size_t(E) * (N + 1), n); }
 
+// Gauss-Jordan with partial pivoting for the scan kernels: same elimination as gauss_jordan() in lq_scan.cuh (row
+// exchange with the largest |pivot|, every other row reduced against the scaled pivot row), laid out for throughput:
+// the scaled pivot row is staged in `prow` once, and each thread then updates 4 x 4 register patches of [W | Rhs]
+// with float4 accesses (no integer division, no per-element index arithmetic), three barriers per pivot plus one
+// when rows are exchanged.  ldw, ldr multiples of 4 and >= the padded row count; W, Rhs, prow 16-byte aligned;
+// prow holds ldw + ldr floats.  Columns of W left of the pivot are dead (never read again) and may be overwritten.
+template <int NT>
+__device__ __forceinline__ void gauss_jordan_tiled(float* W, int ldw, float* Rhs, int ldr, float* v, int k, float* fcol,
+                                                   float* prow, int* s_piv, int tid) {
+  const int RT = (k + 3) >> 2;       // row tiles
+  const int CR = ldr >> 2;           // column chunks of Rhs
+  for (int c = 0; c < k; ++c) {
+    if (tid < 32) {
+      float best = -1.f;
+      int bi = c;
+      for (int i = c + tid; i < k; i += 32) {
+        const float a = fabsf(W[i * ldw + c]);
+        if (a > best || !(a == a)) { best = (a == a) ? a : 3.4e38f; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (tid == 0) *s_piv = bi;
+    }
+    __syncthreads();
+    const int pv = *s_piv;
+    const int c0 = (c + 1) & ~3;       // first live column chunk of W (aligned down: may include dead columns)
+    if (pv != c) {
+      for (int j = c + tid; j < ldw + ldr + 1; j += NT) {
+        float *x, *y;
+        if (j < ldw) { x = W + c * ldw + j; y = W + pv * ldw + j; }
+        else if (j < ldw + ldr) { x = Rhs + c * ldr + (j - ldw); y = Rhs + pv * ldr + (j - ldw); }
+        else { x = v + c; y = v + pv; }
+        const float t = *x; *x = *y; *y = t;
+      }
+      __syncthreads();
+    }
+    {  // multipliers and the scaled pivot row
+      const float inv = 1.f / W[c * ldw + c];
+      for (int j = tid; j < ldw + ldr + 1 + 4 * RT; j += NT) {
+        if (j < ldw) prow[j] = W[c * ldw + j] * inv;
+        else if (j < ldw + ldr) prow[j] = Rhs[c * ldr + (j - ldw)] * inv;
+        else if (j == ldw + ldr) fcol[4 * RT] = v[c] * inv;
+        else { const int i = j - ldw - ldr - 1; fcol[i] = (i < k && i != c) ? W[i * ldw + c] : 0.f; }
+      }
+    }
+    __syncthreads();
+    const int CW = (ldw - c0) >> 2;    // live column chunks of W
+    const int CT = CW + CR;
+    for (int patch = tid; patch < RT * CT; patch += NT) {
+      const int rt = patch / CT, ct = patch - rt * CT;
+      float* base;
+      int ld;
+      const float* pr;
+      if (ct < CW) { base = W + c0 + 4 * ct; ld = ldw; pr = prow + c0 + 4 * ct; }
+      else { base = Rhs + 4 * (ct - CW); ld = ldr; pr = prow + ldw + 4 * (ct - CW); }
+      const float4 pvv = *reinterpret_cast<const float4*>(pr);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * rt + a;
+        float4* cell = reinterpret_cast<float4*>(base + i * ld);
+        if (i == c) {
+          *cell = pvv;
+        } else {
+          const float f = fcol[i];
+          if (f != 0.f || !(f == f)) {
+            float4 x = *cell;
+            x.x = fmaf(-f, pvv.x, x.x); x.y = fmaf(-f, pvv.y, x.y); x.z = fmaf(-f, pvv.z, x.z); x.w = fmaf(-f, pvv.w, x.w);
+            *cell = x;
+          }
+        }
+      }
+    }
+    if (tid < k) {
+      const float vc = fcol[4 * RT];
+      v[tid] = (tid == c) ? vc : fmaf(-fcol[tid], vc, v[tid]);
+    }
+    __syncthreads();
+  }
+}
+
+// C[MT*4, NT*4] = A * B with A [.][lda] and B [.][ldb] row-major, K a multiple of 4 (zero padded): 4 x 4 register tiles,
+// both operands read as float4 (A along k -- a broadcast for the threads that share a tile row --, B along j), i.e.
+// 8 LDS.128 per 64 FMA where gemm_tiles<false, false> issues 16 scalar + 4 vector loads.
+__device__ __forceinline__ void gemm_nn4(float* __restrict__ C, int ldc, const float* __restrict__ A, int lda,
+                                         const float* __restrict__ B, int ldb, int MT, int NT, int K, int tid, int nthreads) {
+  for (int tile = tid; tile < MT * NT; tile += nthreads) {
+    const int i0 = (tile / NT) * 4, j0 = (tile % NT) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+    for (int kk = 0; kk < K; kk += 4) {
+      float av[4][4], bv[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float4 t = *reinterpret_cast<const float4*>(A + (i0 + a) * lda + kk);
+        av[a][0] = t.x; av[a][1] = t.y; av[a][2] = t.z; av[a][3] = t.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(B + (kk + q) * ldb + j0);
+        bv[q][0] = t.x; bv[q][1] = t.y; bv[q][2] = t.z; bv[q][3] = t.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a][q], bv[q][b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      *reinterpret_cast<float4*>(C + (i0 + a) * ldc + j0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  }
+}
+
+// load a [n, n] row-major global matrix TRANSPOSED into a zero-padded [LN][LN] shared tile
+__device__ __forceinline__ void load_padded_t(float* __restrict__ dst, int ld, const float* __restrict__ src, int n, int tid,
+                                              int nthreads) {
+  for (int idx = tid; idx < ld * ld; idx += nthreads) {
+    const int j = idx / ld, i = idx - j * ld;        // consecutive threads read consecutive global addresses src[j][i]
+    if (j < n && i < n) dst[i * ld + j] = src[j * n + i];
+    else dst[idx] = 0.f;                             // (i, j) -> idx is a bijection on the padding as well
+  }
+}
+
 template <int n, int m> struct PscanInitSmem {
   static constexpr int LN = lq_pad(n), LM = lq_pad(m);
   static constexpr int oW = 0;                 // product scratch   [LN][LN]
@@ -42,8 +173,8 @@ template <int n, int m> struct PscanInitSmem {
   static constexpr int oMR = oM + LN * LM;     // M R^-1            [LN][LM]
   static constexpr int oR = oMR + LN * LM;     // R -> chol         [LM][LM]
   static constexpr int oRi = oR + LM * LM;     // R^-1              [LM][LM]
-  static constexpr int oVec = oRi + LM * LM;   // r [LM]
-  static constexpr int total = oVec + LM + 8;
+  static constexpr int oVec = oRi + LM * LM;   // r, GJ dummy rhs vector [LM] ; GJ multipliers [LM + 4] ; pivot row [2 LM] ; pivot
+  static constexpr int total = oVec + 5 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -61,6 +192,10 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
   float* sR = smem + L::oR;
   float* sRi = smem + L::oRi;
   float* sr = smem + L::oVec;
+  float* sdum = sr + LM;
+  float* sfm = sdum + LM;
+  float* sprow = sfm + LM + 4;
+  int* s_piv = reinterpret_cast<int*>(sprow + 2 * LM);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
@@ -80,45 +215,12 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
   load_padded(sB, LM, LN, a.B + kt * n * m, n, m, tid, NT);
   load_padded(sM, LM, LN, a.M + kt * n * m, n, m, tid, NT);
   load_padded(sR, LM, LM, a.R + kt * m * m, m, m, tid, NT);
-  for (int i = tid; i < LM; i += NT) sr[i] = (i < m) ? a.r[kt * m + i] : 0.f;
+  for (int i = tid; i < LM; i += NT) { sr[i] = (i < m) ? a.r[kt * m + i] : 0.f; sdum[i] = 0.f; }
+  for (int idx = tid; idx < LM * LM; idx += NT) sRi[idx] = (idx / LM == idx % LM && idx / LM < m) ? 1.f : 0.f;
   __syncthreads();
-  // R^-1 by Cholesky (primal_tvlqr.py:396-401)
-  if (tid < 32) {
-    for (int j = 0; j < m; ++j) {
-      float d = sR[j * LM + j];
-      for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sR[j * LM + k2], sR[j * LM + k2], d);
-      d = sqrtf(d);
-      const float inv = 1.f / d;
-      __syncwarp();
-      if (tid == 0) sR[j * LM + j] = d;
-      for (int i = j + 1 + tid; i < m; i += 32) {
-        float s = sR[i * LM + j];
-        for (int k2 = 0; k2 < j; ++k2) s = fmaf(-sR[i * LM + k2], sR[j * LM + k2], s);
-        sR[i * LM + j] = s * inv;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  for (int col = tid; col < LM; col += NT) {  // R^-1 column by column: L L' x = e_col
-    float y[m > 0 ? m : 1];
-    if (col < m) {
-#pragma unroll 1
-      for (int i = 0; i < m; ++i) {
-        float s = (i == col) ? 1.f : 0.f;
-        for (int k2 = 0; k2 < i; ++k2) s = fmaf(-sR[i * LM + k2], y[k2], s);
-        y[i] = s / sR[i * LM + i];
-      }
-#pragma unroll 1
-      for (int i = m - 1; i >= 0; --i) {
-        float s = y[i];
-        for (int k2 = i + 1; k2 < m; ++k2) s = fmaf(-sR[k2 * LM + i], y[k2], s);
-        y[i] = s / sR[i * LM + i];
-      }
-    }
-    for (int i = 0; i < LM; ++i) sRi[i * LM + col] = (col < m && i < m) ? y[i] : 0.f;
-  }
-  __syncthreads();
+  // R^-1 (primal_tvlqr.py:396-401 factorises R by Cholesky and solves against I; here the same inverse comes out of
+  // the tiled Gauss-Jordan elimination, m pivots of a few hundred cycles instead of a one-warp factorisation)
+  gauss_jordan_tiled<NT>(sR, LM, sRi, LM, sdum, m, sfm, sprow, s_piv, tid);
   gemm_tiles<false, false>(sBR, LM, sB, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   gemm_tiles<false, false>(sMR, LM, sM, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   __syncthreads();
@@ -157,8 +259,8 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
 template <int n> struct PscanCombineSmem {
   static constexpr int LN = lq_pad(n);
   static constexpr int oS = 0;                   // five [LN][LN] buffers
-  static constexpr int oVec = 5 * LN * LN;       // v / y, u, p_r, c_l, GJ multipliers, scratch  [LN] each ; pivot
-  static constexpr int total = oVec + 6 * LN + 8;
+  static constexpr int oVec = 5 * LN * LN;       // v / y, u, p_r, c_l [LN] each ; GJ multipliers [LN + 4] ; pivot row [2 LN] ; pivot
+  static constexpr int total = oVec + 7 * LN + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -177,8 +279,9 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   float* su = sv + LN;         // c_l - C_l p_r
   float* spr = su + LN;        // p_r
   float* scl = spr + LN;       // c_l
-  float* sf = scl + LN;        // GJ multipliers
-  int* s_piv = reinterpret_cast<int*>(sf + LN + LN);
+  float* sf = scl + LN;        // GJ multipliers [LN + 4]
+  float* sprow = sf + LN + 4;  // GJ scaled pivot row [2 LN]
+  int* s_piv = reinterpret_cast<int*>(sprow + 2 * LN);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (done && done[e]) return;
   const size_t nn = size_t(n) * n;
@@ -204,7 +307,7 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
     scl[i] = (i < n) ? src.c[l * n + i] : 0.f;
   }
   __syncthreads();
-  gemm_tiles<false, false>(S2, LN, S0, LN, S1, LN, TN, TN, n, tid, NT);
+  gemm_nn4(S2, LN, S0, LN, S1, LN, TN, TN, LN, tid, NT);
   for (int idx = tid; idx < 2 * LN; idx += NT) {
     const int i = idx >> 1;
     if (idx & 1) {
@@ -225,14 +328,14 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   for (int i = tid; i < LN; i += NT) S2[i * LN + i] += 1.f;
   __syncthreads();
   // ---- 2: Z' = W^-1 -> S3 ; y = Z' v -> sv
-  gauss_jordan<NT>(S2, LN, S3, LN, n, sv, n, sf, s_piv, tid);
+  gauss_jordan_tiled<NT>(S2, LN, S3, LN, sv, n, sf, sprow, s_piv, tid);
   // ---- 3: X = Z' P_r -> S2
-  gemm_tiles<false, false>(S2, LN, S3, LN, S0, LN, TN, TN, n, tid, NT);
+  gemm_nn4(S2, LN, S3, LN, S0, LN, TN, TN, LN, tid, NT);
   __syncthreads();
   // ---- 4: A_l -> S0 ; T = X A_l -> S4
   load_padded(S0, LN, LN, src.A + l * nn, n, n, tid, NT);
   __syncthreads();
-  gemm_tiles<false, false>(S4, LN, S2, LN, S0, LN, TN, TN, n, tid, NT);
+  gemm_nn4(S4, LN, S2, LN, S0, LN, TN, TN, LN, tid, NT);
   __syncthreads();
   // ---- 5: P = A_l' T + P_l -> S2 -> global ; p = A_l' y + p_l
   gemm_tiles<true, false>(S2, LN, S0, LN, S4, LN, TN, TN, n, tid, NT);
@@ -248,16 +351,16 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   }
   if (r_final) return;  // the new element reaches the terminal knot as well
   __syncthreads();
-  // ---- 6: A_r -> S2 ; Y = A_r Z'^T -> S4
-  load_padded(S2, LN, LN, src.A + r * nn, n, n, tid, NT);
+  // ---- 6: A_r' -> S2 ; Y' = Z' A_r' -> S4   (Y = A_r Z'^T kept transposed: every product below reads rows)
+  load_padded_t(S2, LN, src.A + r * nn, n, tid, NT);
   __syncthreads();
-  gemm_tiles<false, true>(S4, LN, S2, LN, S3, LN, TN, TN, n, tid, NT);
+  gemm_nn4(S4, LN, S3, LN, S2, LN, TN, TN, LN, tid, NT);
   __syncthreads();
   // ---- 7: A = Y A_l -> S3 -> global ; c = Y u + c_r
-  gemm_tiles<false, false>(S3, LN, S4, LN, S0, LN, TN, TN, n, tid, NT);
+  gemm_tiles<true, false>(S3, LN, S4, LN, S0, LN, TN, TN, n, tid, NT);
   for (int i = tid; i < n; i += NT) {
     float s = src.c[r * n + i];
-    for (int j = 0; j < n; ++j) s = fmaf(S4[i * LN + j], su[j], s);
+    for (int j = 0; j < n; ++j) s = fmaf(S4[j * LN + i], su[j], s);
     dst.c[l * n + i] = s;
   }
   __syncthreads();
@@ -266,10 +369,10 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
     dst.A[l * nn + idx] = S3[i * LN + j];
   }
   // ---- 8: D = Y C_l -> S0 (A_l is dead)
-  gemm_tiles<false, false>(S0, LN, S4, LN, S1, LN, TN, TN, n, tid, NT);
+  gemm_tiles<true, false>(S0, LN, S4, LN, S1, LN, TN, TN, n, tid, NT);
   __syncthreads();
   // ---- 9: C = D A_r' + C_r -> S3 -> global
-  gemm_tiles<false, true>(S3, LN, S0, LN, S2, LN, TN, TN, n, tid, NT);
+  gemm_nn4(S3, LN, S0, LN, S2, LN, TN, TN, LN, tid, NT);
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
@@ -287,8 +390,8 @@ template <int n, int m> struct PscanGainSmem {
   static constexpr int oM = oB + LN * LM;       // M                [LN][LM]
   static constexpr int oG = oM + LN * LM;       // G                [LM][LM]
   static constexpr int oR = oG + LM * LM;       // R                [LM][LM]
-  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r, h, GJ multipliers [LM] ; pivot
-  static constexpr int total = oVec + 2 * LN + 3 * LM + 8;
+  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r, h [LM] ; GJ multipliers [LM + 4] ; pivot row [LM + LN] ; pivot
+  static constexpr int total = oVec + 3 * LN + 4 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -310,8 +413,9 @@ __global__ void __launch_bounds__(NT) pscan_gains_kernel(LqArgs a, PscanBuf fin)
   float* sc = sp + LN;
   float* sr = sc + LN;
   float* sh = sr + LM;
-  float* sfm = sh + LM;
-  int* s_piv = reinterpret_cast<int*>(sfm + LM);
+  float* sfm = sh + LM;          // [LM + 4]
+  float* sprow = sfm + LM + 4;   // [LM + LN]
+  int* s_piv = reinterpret_cast<int*>(sprow + LM + LN);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
@@ -354,7 +458,7 @@ __global__ void __launch_bounds__(NT) pscan_gains_kernel(LqArgs a, PscanBuf fin)
   }
   for (int i = tid; i < LM; i += NT) sh[i] = (i < m) ? -sh[i] : 0.f;
   __syncthreads();
-  gauss_jordan<NT>(sG, LM, sH, LN, n, sh, m, sfm, s_piv, tid);  // sH rows 0..m-1 = K, sh = k
+  gauss_jordan_tiled<NT>(sG, LM, sH, LN, sh, m, sfm, sprow, s_piv, tid);  // sH rows 0..m-1 = K, sh = k
   for (int idx = tid; idx < m * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
     a.K[kt * m * n + idx] = sH[i * LN + j];
