@@ -287,7 +287,10 @@ def run_native(args):
     st = synthetic_states(cfg, E, seed=rank)
     T = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
     N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
-    lm = not args.scan
+    # limited_memory as the reference's examples pass it: True for the batched whole-body runs (multi_env.py:44), the
+    # default False for the single-instance controllers and the SRBD wrapper; the wrappers then bind the LQ kernel
+    # that is fastest for the shape (optimizers.wrapper_lq_mode); --scan binds the associative scan literally
+    lm = args.workload in ("go2_wb", "h1_wb") and not args.scan
     if args.scan:
         if args.scan_schedule:
             os.environ["MPXB_SCAN_SCHEDULE"] = args.scan_schedule
@@ -295,7 +298,7 @@ def run_native(args):
 
     if srbd:
         wrap = SrbdWrapper(cfg, E, device=dev)
-        solver = wrap._solver if not lm else __import__("mpx_b200.primal_dual_ilqr.optimizers", fromlist=["MpcSolver"]).MpcSolver(cfg, E, True, device=dev)
+        solver = wrap._solver
         yaw = st["yaw"]
         Ry = np.stack([np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw], 1), np.stack([np.sin(yaw), np.cos(yaw), 0 * yaw], 1),
                        np.stack([0 * yaw, 0 * yaw, 1 + 0 * yaw], 1)], 1)
@@ -473,7 +476,11 @@ def run_native(args):
         except Exception:
             pass
         lq_s = kernel_ms["lq_solve"] * 1e-3
-        roofline = {"kernel": "lq_seq_kernel" if lm else "lq_scan", "bound": "fp32",
+        lq_name = {_lib.LQ_SEQUENTIAL: "sequential", _lib.LQ_SCAN: "scan", _lib.LQ_SCAN_SERIAL: "scan-serial",
+                   _lib.LQ_SCAN_PARALLEL: "scan-parallel"}[solver.lq_mode]
+        if solver.lq_mode == _lib.LQ_SCAN:
+            lq_name = "scan-parallel" if E <= 64 else "scan-serial"
+        roofline = {"kernel": {"sequential": "lq_seq_kernel", "scan-serial": "lq_scan_kernel"}.get(lq_name, "pscan_init + pscan_combine x levels + pscan_gains + pscan_rollout"), "bound": "fp32",
                     "achieved": flq / lq_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": flq / lq_s / 1e12 / fp32_peak, "traffic": traffic,
                     "peak_source": "FP32 FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
@@ -499,7 +506,7 @@ def run_native(args):
                 "warmup": max(Wm, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "robot": robot, "envs_per_gpu": E, "n": n, "m": m, "horizon": N,
-                           "lq": "sequential" if lm else ("scan" + ("-" + args.scan_schedule if args.scan_schedule else "")), "sqp_iterations_per_step": 1,
+                           "lq": lq_name, "limited_memory": lm, "sqp_iterations_per_step": 1,
                            "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
                            "parallelism": f"env-sharded x{world}, no collective on the solve path"},
                 "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,

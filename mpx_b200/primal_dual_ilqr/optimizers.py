@@ -35,19 +35,42 @@ def _unwrap(p):
     return p, args
 
 
-def wrapper_lq_is_sequential(limited_memory):
-    """Which LQ kernel the controller wrappers bind.
+# measured on B200 at E = 1 (profiles/r01ah_launches_*_pscan.csv, r01ai_launches_*_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
+# n -> (sequential kernel per knot, parallel-scan combine per level, parallel-scan fixed part, its rollout per knot)
+_LQ_COST_US = {13: (8.9, 22.0, 37.0, 1.2), 61: (18.0, 104.0, 76.0, 2.6), 75: (30.5, 161.5, 107.0, 3.3),
+               81: (79.0, 197.0, 280.0, 4.1)}
+
+
+def wrapper_lq_mode(limited_memory, n_env, n, N):
+    """Which LQ kernel the controller wrappers bind (an ``_lib.LQ_*`` value).
 
     The reference picks the associative-scan Riccati (`tvlqr_gpu`) when ``limited_memory=False`` because on an XLA
-    GPU the sequential recursion is launch-latency bound.  Here both forms are single kernels and solve the same LQ
-    problem to rounding; on B200 the sequential kernel is faster for every shipped configuration (measured, E=1:
-    Talos 18.4 ms scan vs. sub-millisecond sequential; SRBD 0.96 ms vs. ~0.1 ms), so the wrappers bind it regardless of
-    ``limited_memory``.  ``MPXB_LQ=scan`` in the environment restores the literal mapping; ``MpcSolver`` itself always
-    maps ``limited_memory`` literally (the parity tests exercise both kernels through it)."""
+    GPU the sequential recursion is launch-latency bound.  Here every form solves the same LQ problem to rounding,
+    so for ``limited_memory=False`` the wrappers bind whichever is faster on B200 for the shape at hand:
+
+    * ``limited_memory=True`` -> the sequential kernel, literally (examples/multi_env.py:44);
+    * ``limited_memory=False`` -> the scan scheduled in parallel over the horizon (one CTA per knot, log2 levels) when
+      its modelled time  fixed + levels x waves x combine  beats  N x knot  of the sequential kernel, with the
+      per-size constants measured at E = 1 (``_LQ_COST_US``; waves = ceil(n_env (N + 1) / 148)): single instances of
+      the SRBD model (tick 0.23 vs 0.28 ms) and of Talos (N = 25: LQ 1.28 vs 1.99 ms; N = 200: 3.7 vs 15.3 ms), long
+      horizons in general; Aliengo / Go2 at N = 25 (0.62 vs 0.45 ms) and every large batch stay on the sequential
+      kernel, where one CTA per environment already fills the GPU and the scan's ~9x FLOPs buy nothing.
+
+    ``MPXB_LQ=scan`` in the environment restores the literal mapping (``LQ_SCAN``), ``MPXB_LQ=sequential`` forces the
+    sequential kernel; ``MpcSolver`` itself always maps ``limited_memory`` literally (the parity tests exercise every
+    kernel through it)."""
     import os
-    if os.environ.get("MPXB_LQ", "").lower() == "scan":
-        return bool(limited_memory)
-    return True
+    forced = os.environ.get("MPXB_LQ", "").lower()
+    if forced == "scan":
+        return _lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN
+    if forced == "sequential" or limited_memory or n_env > 64 or n not in _LQ_COST_US:
+        return _lib.LQ_SEQUENTIAL
+    knot, comb, fixed, roll = _LQ_COST_US[n]
+    levels = int(N).bit_length()
+    waves = -(-n_env * (N + 1) // 148)
+    t_scan = fixed + roll * N + levels * waves * comb
+    t_seq = N * knot
+    return _lib.LQ_SCAN_PARALLEL if t_scan < t_seq else _lib.LQ_SEQUENTIAL
 
 
 class MpcSolver:
@@ -61,7 +84,7 @@ class MpcSolver:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.n_env = int(n_env)
         self.lq_mode = (_lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN) if lq_mode is None else int(lq_mode)
-        if lq_mode is None and not limited_memory:
+        if self.lq_mode == _lib.LQ_SCAN:
             # MPXB_SCAN_SCHEDULE=serial|parallel forces a schedule of the associative scan (benchmarks / profiling)
             import os
             forced = {"serial": _lib.LQ_SCAN_SERIAL, "parallel": _lib.LQ_SCAN_PARALLEL}.get(

@@ -71,8 +71,8 @@ class _Base:
         self.dynamics = partial(config.dynamics, self.model, None, config.contact_frame, config.body_name,
                                 config.n_joints, config.dt)
         self.work = partial(optimizers.mpc, self.cost, self.dynamics, hessian_approx, limited_memory)
-        self._solver = optimizers.MpcSolver(config, n_env, limited_memory=optimizers.wrapper_lq_is_sequential(limited_memory),
-                                            device=self.device,
+        self._solver = optimizers.MpcSolver(config, n_env, device=self.device,
+                                            lq_mode=optimizers.wrapper_lq_mode(limited_memory, n_env, config.n, config.N),
                                             robot_model=self.model, max_iter=max_iter)
         self.u_ref = self._T(config.u_ref)
         self.W = self._T(config.W)
@@ -248,7 +248,7 @@ class MPCControllerWrapper(_Base):
         parameter = self._as(np.asarray(parameter))[None].contiguous()
         nq = 13 + cfg.n_joints
         self.X0[:, :, :nq] = reference[:, :, :nq]
-        solver = optimizers.MpcSolver(cfg, 1, limited_memory=self._solver.lq_mode == _lib.LQ_SEQUENTIAL,
+        solver = optimizers.MpcSolver(cfg, 1, lq_mode=self._solver.lq_mode,
                                       device=self.device, robot_model=self.model, max_iter=max_iter)
         X, U, V = solver.solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
         self.X0, self.U0, self.V0 = X, U, V

@@ -39,8 +39,8 @@ class BatchedMPCControllerWrapper:
         dynamics = partial(mpc_dyn_model.quadruped_srbd_dynamics, config.mass, inertia, np.linalg.inv(inertia), config.dt)
         self.work = partial(optimizers.mpc, cost, dynamics, hessian_approx, False)
         # the batch axis of the CUDA solver replaces jax.jit(jax.vmap(work)) (mpc_wrapper_srbd.py:77)
-        self._solver = optimizers.MpcSolver(config, n_env, limited_memory=optimizers.wrapper_lq_is_sequential(False),
-                                            device=self.device)
+        self._solver = optimizers.MpcSolver(config, n_env, device=self.device,
+                                            lq_mode=optimizers.wrapper_lq_mode(False, n_env, config.n, config.N))
         self._solve = self._solver.solve
         self._ref_gen = partial(mpc_utils.reference_generator_srbd, config.use_terrain_estimator, config.N, config.dt,
                                 config.n_contact, mass=config.mass, clearence_speed=config.clearence_speed,
