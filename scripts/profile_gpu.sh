@@ -11,3 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"linearize|lq_seq|lq_scan|trial|select_update" --launch-skip 24 -c 8 \
     -f -o gpurun_out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-latency --prewarm-s 0 "$@" > gpurun_out/${tag}_full_bench.log 2>&1
 ls -la gpurun_out
+# parallel-in-time LQ (Talos single instance): one full tick's pscan kernels
+ncu --set full --clock-control none --import-source on -k regex:"pscan" --launch-skip 32 -c 8 \
+    -f -o gpurun_out/${tag}_pscan_talos python bench.py --workload talos_wb --envs 1 --steps 2 --warmup 3 --no-cpu-baseline --no-latency --prewarm-s 0 > gpurun_out/${tag}_pscan_talos_bench.log 2>&1
+ls -la gpurun_out | tail -5
