@@ -479,8 +479,9 @@ __global__ void __launch_bounds__(NT) pscan_rollout_kernel(LqArgs a, int arena) 
 }
 
 template <int n, int m> cudaError_t launch_lq_pscan(const LqArgs& a, float* ws, cudaStream_t st) {
-  // threads per CTA: barriers dominate the small sizes (SRBD: 16 tiles per product), so those run two warps
-  constexpr int NT = n <= 16 ? 64 : 256, NTC = n <= 16 ? 64 : (n <= 32 ? 128 : 512);
+  // threads per CTA: 256 / 512 also for the small sizes (two-warp CTAs measured slower for SRBD, tick 0.26 vs 0.23 ms:
+  // the kernels are bound by load and barrier latency, which more warps overlap)
+  constexpr int NT = 256, NTC = 512;
   static_assert(NT >= n || n > 256, "rollout / elimination index rows by thread");
   static_assert(NTC >= n && NT >= m, "gauss_jordan_tiled updates the right-hand-side vector one row per thread");
   auto k_init = pscan_init_kernel<n, m, NT>;
