@@ -116,6 +116,76 @@ __device__ __forceinline__ void gauss_jordan_tiled(float* W, int ldw, float* Rhs
   }
 }
 
+// Gauss-Jordan with partial pivoting, OUT OF PLACE: pivot step c reads [W | Rhs | v] from buffer c & 1 and writes the
+// whole updated system to the other buffer, so nothing is staged and nothing is exchanged in place -- the row swap is
+// a renaming of the source rows -- and a pivot costs ONE barrier (gauss_jordan_tiled: three or four, each a full
+// shared-memory round trip, which is what an 81-pivot elimination is made of).  Every warp finds the pivot itself
+// (three loads and a shuffle butterfly on (|value| bits, ~row) packed in 64 bits; ties to the smallest row, NaN wins
+// and propagates), every thread scales its own chunk of the pivot row.  Same arithmetic as gauss_jordan_tiled.
+// Buffers: W[2] [.][ldw], Rhs[2] [.][ldr], v[2]; ldw, ldr multiples of 4, rows padded to a multiple of 4 (padded rows
+// carry zeros in the pivot columns and are copied through); the result is in buffer k & 1.
+template <int NT>
+__device__ __forceinline__ void gauss_jordan_pp(float* W0, float* W1, int ldw, float* R0, float* R1, int ldr, float* v0,
+                                                float* v1, int k, int tid) {
+  const int RT = (k + 3) >> 2;
+  const int CR = ldr >> 2;
+  const int lane = tid & 31;
+  for (int c = 0; c < k; ++c) {
+    const float* Wo = (c & 1) ? W1 : W0;
+    float* Wn = (c & 1) ? W0 : W1;
+    const float* Ro = (c & 1) ? R1 : R0;
+    float* Rn = (c & 1) ? R0 : R1;
+    const float* vo = (c & 1) ? v1 : v0;
+    float* vn = (c & 1) ? v0 : v1;
+    unsigned long long best = 0ull;
+    for (int i = c + lane; i < k; i += 32) {
+      const unsigned long long pk = (static_cast<unsigned long long>(__float_as_uint(fabsf(Wo[i * ldw + c]))) << 32) |
+                                    static_cast<unsigned>(0x7fffffff - i);
+      best = pk > best ? pk : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      best = ob > best ? ob : best;
+    }
+    const int pv = 0x7fffffff - static_cast<int>(static_cast<unsigned>(best & 0xffffffffull));
+    const float inv = 1.f / Wo[pv * ldw + c];
+    const int c0 = (c + 1) & ~3;       // first live column chunk of W (aligned down: may include dead columns)
+    const int CW = (ldw - c0) >> 2;
+    const int CT = CW + CR;
+    for (int patch = tid; patch < RT * CT; patch += NT) {
+      const int rt = patch / CT, ct = patch - rt * CT;
+      const float* ob;
+      float* nb;
+      int ld;
+      if (ct < CW) { ob = Wo + c0 + 4 * ct; nb = Wn + c0 + 4 * ct; ld = ldw; }
+      else { ob = Ro + 4 * (ct - CW); nb = Rn + 4 * (ct - CW); ld = ldr; }
+      float4 pr = *reinterpret_cast<const float4*>(ob + pv * ld);
+      pr.x *= inv; pr.y *= inv; pr.z *= inv; pr.w *= inv;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * rt + a;
+        float4 x;
+        if (i == c) {
+          x = pr;
+        } else {
+          const int src = (i == pv) ? c : i;     // the exchanged row
+          const float f = Wo[src * ldw + c];
+          x = *reinterpret_cast<const float4*>(ob + src * ld);
+          x.x = fmaf(-f, pr.x, x.x); x.y = fmaf(-f, pr.y, x.y); x.z = fmaf(-f, pr.z, x.z); x.w = fmaf(-f, pr.w, x.w);
+        }
+        *reinterpret_cast<float4*>(nb + i * ld) = x;
+      }
+    }
+    if (tid < 4 * RT) {
+      const float vc = vo[pv] * inv;
+      const int src = (tid == pv) ? c : tid;
+      vn[tid] = (tid == c) ? vc : fmaf(-Wo[src * ldw + c], vc, vo[src]);
+    }
+    __syncthreads();
+  }
+}
+
 // C[MT*4, NT*4] = A * B with A [.][lda] and B [.][ldb] row-major, K a multiple of 4 (zero padded): 4 x 4 register tiles,
 // both operands read as float4 (A along k -- a broadcast for the threads that share a tile row --, B along j), i.e.
 // 8 LDS.128 per 64 FMA where gemm_tiles<false, false> issues 16 scalar + 4 vector loads.
@@ -171,10 +241,10 @@ template <int n, int m> struct PscanInitSmem {
   static constexpr int oBR = oB + LN * LM;     // B R^-1            [LN][LM]
   static constexpr int oM = oBR + LN * LM;     // M                 [LN][LM]
   static constexpr int oMR = oM + LN * LM;     // M R^-1            [LN][LM]
-  static constexpr int oR = oMR + LN * LM;     // R -> chol         [LM][LM]
-  static constexpr int oRi = oR + LM * LM;     // R^-1              [LM][LM]
-  static constexpr int oVec = oRi + LM * LM;   // r, GJ dummy rhs vector [LM] ; GJ multipliers [LM + 4] ; pivot row [2 LM] ; pivot
-  static constexpr int total = oVec + 5 * LM + 16;
+  static constexpr int oR = oMR + LN * LM;     // R                 [2][LM][LM]
+  static constexpr int oRi = oR + 2 * LM * LM; // I -> R^-1         [2][LM][LM]  (R, R^-1: ping-pong pairs of the elimination)
+  static constexpr int oVec = oRi + 2 * LM * LM;  // r [LM] ; dummy right-hand-side vector [2][LM]
+  static constexpr int total = oVec + 3 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -193,9 +263,6 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
   float* sRi = smem + L::oRi;
   float* sr = smem + L::oVec;
   float* sdum = sr + LM;
-  float* sfm = sdum + LM;
-  float* sprow = sfm + LM + 4;
-  int* s_piv = reinterpret_cast<int*>(sprow + 2 * LM);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
@@ -215,12 +282,13 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
   load_padded(sB, LM, LN, a.B + kt * n * m, n, m, tid, NT);
   load_padded(sM, LM, LN, a.M + kt * n * m, n, m, tid, NT);
   load_padded(sR, LM, LM, a.R + kt * m * m, m, m, tid, NT);
-  for (int i = tid; i < LM; i += NT) { sr[i] = (i < m) ? a.r[kt * m + i] : 0.f; sdum[i] = 0.f; }
+  for (int i = tid; i < LM; i += NT) { sr[i] = (i < m) ? a.r[kt * m + i] : 0.f; sdum[i] = 0.f; sdum[LM + i] = 0.f; }
   for (int idx = tid; idx < LM * LM; idx += NT) sRi[idx] = (idx / LM == idx % LM && idx / LM < m) ? 1.f : 0.f;
   __syncthreads();
   // R^-1 (primal_tvlqr.py:396-401 factorises R by Cholesky and solves against I; here the same inverse comes out of
-  // the tiled Gauss-Jordan elimination, m pivots of a few hundred cycles instead of a one-warp factorisation)
-  gauss_jordan_tiled<NT>(sR, LM, sRi, LM, sdum, m, sfm, sprow, s_piv, tid);
+  // the Gauss-Jordan elimination, m pivots of a few hundred cycles instead of a one-warp factorisation)
+  gauss_jordan_pp<NT>(sR, sR + LM * LM, LM, sRi, sRi + LM * LM, LM, sdum, sdum + LM, m, tid);
+  if (m & 1) sRi += LM * LM;
   gemm_tiles<false, false>(sBR, LM, sB, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   gemm_tiles<false, false>(sMR, LM, sM, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   __syncthreads();
@@ -258,9 +326,9 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
 
 template <int n> struct PscanCombineSmem {
   static constexpr int LN = lq_pad(n);
-  static constexpr int oS = 0;                   // five [LN][LN] buffers
-  static constexpr int oVec = 5 * LN * LN;       // v / y, u, p_r, c_l [LN] each ; GJ multipliers [LN + 4] ; pivot row [2 LN] ; pivot
-  static constexpr int total = oVec + 7 * LN + 16;
+  static constexpr int oS = 0;                   // six [LN][LN] buffers
+  static constexpr int oVec = 6 * LN * LN;       // v / y [2][LN], u, p_r, c_l [LN] each
+  static constexpr int total = oVec + 5 * LN + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -275,13 +343,11 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   float* S2 = S1 + LN * LN;
   float* S3 = S2 + LN * LN;
   float* S4 = S3 + LN * LN;
-  float* sv = smem + L::oVec;  // p_r + P_r c_l  ->  y = Z' (...)
-  float* su = sv + LN;         // c_l - C_l p_r
+  float* S5 = S4 + LN * LN;
+  float* sv = smem + L::oVec;  // p_r + P_r c_l  ->  y = Z' (...)   [2][LN]: ping-pong of the elimination
+  float* su = sv + 2 * LN;     // c_l - C_l p_r
   float* spr = su + LN;        // p_r
   float* scl = spr + LN;       // c_l
-  float* sf = scl + LN;        // GJ multipliers [LN + 4]
-  float* sprow = sf + LN + 4;  // GJ scaled pivot row [2 LN]
-  int* s_piv = reinterpret_cast<int*>(sprow + 2 * LN);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (done && done[e]) return;
   const size_t nn = size_t(n) * n;
@@ -327,8 +393,9 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   __syncthreads();
   for (int i = tid; i < LN; i += NT) S2[i * LN + i] += 1.f;
   __syncthreads();
-  // ---- 2: Z' = W^-1 -> S3 ; y = Z' v -> sv
-  gauss_jordan_tiled<NT>(S2, LN, S3, LN, sv, n, sf, sprow, s_piv, tid);
+  // ---- 2: Z' = W^-1 ; y = Z' v   (ping-pong pairs (S2, S4), (S3, S5), sv[2]; the result lands in buffer n & 1)
+  gauss_jordan_pp<NT>(S2, S4, LN, S3, S5, LN, sv, sv + LN, n, tid);
+  if (n & 1) { float* t = S3; S3 = S5; S5 = t; sv += LN; }   // S3 = Z', S5 = scratch from here on
   // ---- 3: X = Z' P_r -> S2
   gemm_nn4(S2, LN, S3, LN, S0, LN, TN, TN, LN, tid, NT);
   __syncthreads();
@@ -356,8 +423,8 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   __syncthreads();
   gemm_nn4(S4, LN, S3, LN, S2, LN, TN, TN, LN, tid, NT);
   __syncthreads();
-  // ---- 7: A = Y A_l -> S3 -> global ; c = Y u + c_r
-  gemm_tiles<true, false>(S3, LN, S4, LN, S0, LN, TN, TN, n, tid, NT);
+  // ---- 7: A = Y A_l -> S5 -> global ; c = Y u + c_r
+  gemm_tiles<true, false>(S5, LN, S4, LN, S0, LN, TN, TN, n, tid, NT);
   for (int i = tid; i < n; i += NT) {
     float s = src.c[r * n + i];
     for (int j = 0; j < n; ++j) s = fmaf(S4[j * LN + i], su[j], s);
@@ -366,7 +433,7 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
-    dst.A[l * nn + idx] = S3[i * LN + j];
+    dst.A[l * nn + idx] = S5[i * LN + j];
   }
   // ---- 8: D = Y C_l -> S0 (A_l is dead)
   gemm_tiles<true, false>(S0, LN, S4, LN, S1, LN, TN, TN, n, tid, NT);
@@ -384,14 +451,14 @@ template <int n, int m> struct PscanGainSmem {
   static constexpr int LN = lq_pad(n), LM = lq_pad(m);
   static constexpr int oP = 0;                  // P_{t+1}          [LN][LN]
   static constexpr int oA = oP + LN * LN;       // A_t              [LN][LN]
-  static constexpr int oH = oA + LN * LN;       // H -> K           [LM][LN]
-  static constexpr int oBtP = oH + LM * LN;     // B' P+            [LM][LN]
+  static constexpr int oH = oA + LN * LN;       // H -> K           [2][LM][LN]  (G, H, h: ping-pong pairs of the elimination)
+  static constexpr int oBtP = oH + 2 * LM * LN; // B' P+            [LM][LN]
   static constexpr int oB = oBtP + LM * LN;     // B                [LN][LM]
   static constexpr int oM = oB + LN * LM;       // M                [LN][LM]
-  static constexpr int oG = oM + LN * LM;       // G                [LM][LM]
-  static constexpr int oR = oG + LM * LM;       // R                [LM][LM]
-  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r, h [LM] ; GJ multipliers [LM + 4] ; pivot row [LM + LN] ; pivot
-  static constexpr int total = oVec + 3 * LN + 4 * LM + 16;
+  static constexpr int oG = oM + LN * LM;       // G                [2][LM][LM]
+  static constexpr int oR = oG + 2 * LM * LM;   // R                [LM][LM]
+  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r [LM] ; h [2][LM]
+  static constexpr int total = oVec + 2 * LN + 3 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -413,9 +480,6 @@ __global__ void __launch_bounds__(NT) pscan_gains_kernel(LqArgs a, PscanBuf fin)
   float* sc = sp + LN;
   float* sr = sc + LN;
   float* sh = sr + LM;
-  float* sfm = sh + LM;          // [LM + 4]
-  float* sprow = sfm + LM + 4;   // [LM + LN]
-  int* s_piv = reinterpret_cast<int*>(sprow + LM + LN);
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
@@ -458,7 +522,8 @@ __global__ void __launch_bounds__(NT) pscan_gains_kernel(LqArgs a, PscanBuf fin)
   }
   for (int i = tid; i < LM; i += NT) sh[i] = (i < m) ? -sh[i] : 0.f;
   __syncthreads();
-  gauss_jordan_tiled<NT>(sG, LM, sH, LN, sh, m, sfm, sprow, s_piv, tid);  // sH rows 0..m-1 = K, sh = k
+  gauss_jordan_pp<NT>(sG, sG + LM * LM, LM, sH, sH + LM * LN, LN, sh, sh + LM, m, tid);
+  if (m & 1) { sH += LM * LN; sh += LM; }                                  // sH rows 0..m-1 = K, sh = k
   for (int idx = tid; idx < m * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
     a.K[kt * m * n + idx] = sH[i * LN + j];
