@@ -186,6 +186,116 @@ __device__ __forceinline__ void gauss_jordan_pp(float* W0, float* W1, int ldw, f
   }
 }
 
+// Gauss-Jordan with partial pivoting, REGISTER RESIDENT: every thread keeps its 4 x 4 patches of [W | Rhs | v] in
+// registers for the whole elimination (two patches per thread at the shipped sizes); per pivot the owners of column c
+// publish it (fcol), every warp finds the pivot among the rows not used yet, the owners of the pivot row publish it
+// (prow), and each thread updates its own registers: ~40 instructions and two barriers per pivot where the
+// shared-memory forms (gauss_jordan_tiled / _pp) spend ~250 instructions per warp on addressing and staging.  Rows are
+// never exchanged: the pivot row stays where it is, is marked used, and the rows are written back permuted at the end
+// (same pivots, same arithmetic as the exchange form).  fcol / prow are double-buffered by the parity of the pivot.
+// W [LDW rows][LDW], R [LDW rows][LDR] (in: right-hand sides, out: W^-1 R), v [LDW] (in / out); k <= LDW pivots;
+// rows >= k must carry zeros in the pivot columns.  scratch: 2 * (LDW + LDW + LDR + 4) floats + 2 * LDW ints.
+template <int NT, int LDW, int LDR>
+__device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, int k, float* scratch, int tid) {
+  constexpr int RT = LDW / 4, CW = LDW / 4, CR = LDR / 4, CT = CW + CR + 1, NP = RT * CT, PPT = (NP + NT - 1) / NT;
+  constexpr int PROW = LDW + LDR + 4;
+  float* fcol = scratch;                    // [2][LDW]
+  float* prow = scratch + 2 * LDW;          // [2][PROW]
+  int* used = reinterpret_cast<int*>(prow + 2 * PROW);   // [LDW]
+  int* colof = used + LDW;                  // [LDW]: physical row -> the pivot column it served
+  const int lane = tid & 31;
+  float4 reg[PPT][4];
+  int prt[PPT], pct[PPT];
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int p = tid + q * NT;
+    prt[q] = p < NP ? p / CT : -1;
+    pct[q] = p < NP ? p - (p / CT) * CT : -1;
+    if (prt[q] >= 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * prt[q] + a;
+        if (pct[q] < CW) reg[q][a] = *reinterpret_cast<const float4*>(W + i * LDW + 4 * pct[q]);
+        else if (pct[q] < CW + CR) reg[q][a] = *reinterpret_cast<const float4*>(R + i * LDR + 4 * (pct[q] - CW));
+        else reg[q][a] = make_float4(v[i], 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  for (int i = tid; i < LDW; i += NT) { used[i] = 0; colof[i] = i; }
+  for (int c = 0; c < k; ++c) {
+    float* fc = fcol + (c & 1) * LDW;
+    float* pw = prow + (c & 1) * PROW;
+    // column c, from its owners
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+      if (pct[q] == (c >> 2)) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 x = reg[q][a];
+          const int w = c & 3;
+          fc[4 * prt[q] + a] = w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w));
+        }
+      }
+    __syncthreads();
+    unsigned long long best = 0ull;
+    for (int i = lane; i < k; i += 32)
+      if (!used[i]) {
+        const unsigned long long pk = (static_cast<unsigned long long>(__float_as_uint(fabsf(fc[i]))) << 32) |
+                                      static_cast<unsigned>(0x7fffffff - i);
+        best = pk > best ? pk : best;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      best = ob > best ? ob : best;
+    }
+    const int pv = 0x7fffffff - static_cast<int>(static_cast<unsigned>(best & 0xffffffffull));
+    // the pivot row, from its owners
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+      if (prt[q] == (pv >> 2)) {
+        const int a = pv & 3;
+        const float4 x = a == 0 ? reg[q][0] : (a == 1 ? reg[q][1] : (a == 2 ? reg[q][2] : reg[q][3]));
+        *reinterpret_cast<float4*>(pw + 4 * pct[q]) = x;
+      }
+    __syncthreads();
+    if (tid == 0) { used[pv] = 1; colof[pv] = c; }   // read again only after the next barrier
+    const float inv = 1.f / fc[pv];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      if (prt[q] < 0) continue;
+      if (pct[q] < CW && 4 * pct[q] + 3 < c) continue;   // columns of W left of the pivot are dead
+      float4 pr = *reinterpret_cast<const float4*>(pw + 4 * pct[q]);
+      pr.x *= inv; pr.y *= inv; pr.z *= inv; pr.w *= inv;
+      const float4 f4 = *reinterpret_cast<const float4*>(fc + 4 * prt[q]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float f = a == 0 ? f4.x : (a == 1 ? f4.y : (a == 2 ? f4.z : f4.w));
+        if (4 * prt[q] + a == pv) {
+          reg[q][a] = pr;
+        } else {
+          float4 x = reg[q][a];
+          x.x = fmaf(-f, pr.x, x.x); x.y = fmaf(-f, pr.y, x.y); x.z = fmaf(-f, pr.z, x.z); x.w = fmaf(-f, pr.w, x.w);
+          reg[q][a] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // write back W^-1 R and W^-1 v, rows in pivot order
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    if (prt[q] < 0 || pct[q] < CW) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int row = colof[4 * prt[q] + a];
+      if (pct[q] < CW + CR) *reinterpret_cast<float4*>(R + row * LDR + 4 * (pct[q] - CW)) = reg[q][a];
+      else v[row] = reg[q][a].x;
+    }
+  }
+  __syncthreads();
+}
+
 // C[MT*4, NT*4] = A * B with A [.][lda] and B [.][ldb] row-major, K a multiple of 4 (zero padded): 4 x 4 register tiles,
 // both operands read as float4 (A along k -- a broadcast for the threads that share a tile row --, B along j), i.e.
 // 8 LDS.128 per 64 FMA where gemm_tiles<false, false> issues 16 scalar + 4 vector loads.
@@ -243,8 +353,8 @@ template <int n, int m> struct PscanInitSmem {
   static constexpr int oMR = oM + LN * LM;     // M R^-1            [LN][LM]
   static constexpr int oR = oMR + LN * LM;     // R                 [2][LM][LM]
   static constexpr int oRi = oR + 2 * LM * LM; // I -> R^-1         [2][LM][LM]  (R, R^-1: ping-pong pairs of the elimination)
-  static constexpr int oVec = oRi + 2 * LM * LM;  // r [LM] ; dummy right-hand-side vector [2][LM]
-  static constexpr int total = oVec + 3 * LM + 16;
+  static constexpr int oVec = oRi + 2 * LM * LM;  // r [LM] ; dummy right-hand-side vector [LM] ; elimination scratch [8 LM + 8]
+  static constexpr int total = oVec + 10 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -287,8 +397,7 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
   __syncthreads();
   // R^-1 (primal_tvlqr.py:396-401 factorises R by Cholesky and solves against I; here the same inverse comes out of
   // the Gauss-Jordan elimination, m pivots of a few hundred cycles instead of a one-warp factorisation)
-  gauss_jordan_pp<NT>(sR, sR + LM * LM, LM, sRi, sRi + LM * LM, LM, sdum, sdum + LM, m, tid);
-  if (m & 1) sRi += LM * LM;
+  gauss_jordan_reg<NT, LM, LM>(sR, sRi, sdum, m, sdum + LM, tid);
   gemm_tiles<false, false>(sBR, LM, sB, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   gemm_tiles<false, false>(sMR, LM, sM, LM, sRi, LM, LN / 4, LM / 4, m, tid, NT);
   __syncthreads();
@@ -327,8 +436,8 @@ __global__ void __launch_bounds__(NT) pscan_init_kernel(LqArgs a, PscanBuf o) {
 template <int n> struct PscanCombineSmem {
   static constexpr int LN = lq_pad(n);
   static constexpr int oS = 0;                   // six [LN][LN] buffers
-  static constexpr int oVec = 6 * LN * LN;       // v / y [2][LN], u, p_r, c_l [LN] each
-  static constexpr int total = oVec + 5 * LN + 16;
+  static constexpr int oVec = 6 * LN * LN;       // v / y, u, p_r, c_l [LN] each ; elimination scratch [8 LN + 8]
+  static constexpr int total = oVec + 12 * LN + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -344,10 +453,11 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   float* S3 = S2 + LN * LN;
   float* S4 = S3 + LN * LN;
   float* S5 = S4 + LN * LN;
-  float* sv = smem + L::oVec;  // p_r + P_r c_l  ->  y = Z' (...)   [2][LN]: ping-pong of the elimination
-  float* su = sv + 2 * LN;     // c_l - C_l p_r
+  float* sv = smem + L::oVec;  // p_r + P_r c_l  ->  y = Z' (...)
+  float* su = sv + LN;         // c_l - C_l p_r
   float* spr = su + LN;        // p_r
   float* scl = spr + LN;       // c_l
+  float* sscr = scl + LN;      // elimination scratch
   const int t = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   if (done && done[e]) return;
   const size_t nn = size_t(n) * n;
@@ -393,9 +503,8 @@ __global__ void __launch_bounds__(NT) pscan_combine_kernel(int N, int d, const i
   __syncthreads();
   for (int i = tid; i < LN; i += NT) S2[i * LN + i] += 1.f;
   __syncthreads();
-  // ---- 2: Z' = W^-1 ; y = Z' v   (ping-pong pairs (S2, S4), (S3, S5), sv[2]; the result lands in buffer n & 1)
-  gauss_jordan_pp<NT>(S2, S4, LN, S3, S5, LN, sv, sv + LN, n, tid);
-  if (n & 1) { float* t = S3; S3 = S5; S5 = t; sv += LN; }   // S3 = Z', S5 = scratch from here on
+  // ---- 2: Z' = W^-1 -> S3 ; y = Z' v -> sv   (register-resident elimination)
+  gauss_jordan_reg<NT, LN, LN>(S2, S3, sv, n, sscr, tid);
   // ---- 3: X = Z' P_r -> S2
   gemm_nn4(S2, LN, S3, LN, S0, LN, TN, TN, LN, tid, NT);
   __syncthreads();
@@ -457,8 +566,8 @@ template <int n, int m> struct PscanGainSmem {
   static constexpr int oM = oB + LN * LM;       // M                [LN][LM]
   static constexpr int oG = oM + LN * LM;       // G                [2][LM][LM]
   static constexpr int oR = oG + 2 * LM * LM;   // R                [LM][LM]
-  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r [LM] ; h [2][LM]
-  static constexpr int total = oVec + 2 * LN + 3 * LM + 16;
+  static constexpr int oVec = oR + LM * LM;     // p+, c [LN] ; r, h [LM] ; elimination scratch [6 LM + 2 LN + 8]
+  static constexpr int total = oVec + 4 * LN + 8 * LM + 16;
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
@@ -522,8 +631,7 @@ __global__ void __launch_bounds__(NT) pscan_gains_kernel(LqArgs a, PscanBuf fin)
   }
   for (int i = tid; i < LM; i += NT) sh[i] = (i < m) ? -sh[i] : 0.f;
   __syncthreads();
-  gauss_jordan_pp<NT>(sG, sG + LM * LM, LM, sH, sH + LM * LN, LN, sh, sh + LM, m, tid);
-  if (m & 1) { sH += LM * LN; sh += LM; }                                  // sH rows 0..m-1 = K, sh = k
+  gauss_jordan_reg<NT, LM, LN>(sG, sH, sh, m, sh + LM, tid);               // sH rows 0..m-1 = K, sh = k
   for (int idx = tid; idx < m * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
     a.K[kt * m * n + idx] = sH[i * LN + j];

@@ -35,10 +35,10 @@ def _unwrap(p):
     return p, args
 
 
-# measured on B200 at E = 1 (profiles/r01ah_launches_*_pscan.csv, r01ai_launches_*_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
+# measured on B200 at E = 1 (profiles/r01ao_launches_*_e1_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
 # n -> (sequential kernel per knot, parallel-scan combine per level, parallel-scan fixed part, its rollout per knot)
-_LQ_COST_US = {13: (8.9, 22.0, 37.0, 1.2), 61: (18.0, 104.0, 76.0, 2.6), 75: (30.5, 161.5, 107.0, 3.3),
-               81: (79.0, 197.0, 280.0, 4.1)}
+_LQ_COST_US = {13: (8.9, 18.4, 31.0, 1.2), 61: (18.0, 105.0, 70.0, 2.7), 75: (30.5, 145.0, 99.0, 3.4),
+               81: (79.0, 175.0, 273.0, 4.0)}
 
 
 def wrapper_lq_mode(limited_memory, n_env, n, N):
