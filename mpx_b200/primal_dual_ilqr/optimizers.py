@@ -37,8 +37,8 @@ def _unwrap(p):
 
 # measured on B200 at E = 1 (profiles/r01ao_launches_*_e1_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
 # n -> (sequential kernel per knot, parallel-scan combine per level, parallel-scan fixed part, its rollout per knot)
-_LQ_COST_US = {13: (8.9, 18.4, 31.0, 1.2), 61: (18.0, 105.0, 70.0, 2.7), 75: (30.5, 145.0, 99.0, 3.4),
-               81: (79.0, 175.0, 273.0, 4.0)}
+_LQ_COST_US = {13: (8.9, 16.9, 28.0, 1.2), 61: (18.0, 102.0, 68.0, 2.7), 75: (30.5, 144.0, 97.0, 3.4),
+               81: (79.0, 171.0, 251.0, 4.1)}
 
 
 def wrapper_lq_mode(limited_memory, n_env, n, N):
