@@ -201,8 +201,7 @@ __device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, i
   constexpr int PROW = LDW + LDR + 4;
   float* fcol = scratch;                    // [2][LDW]
   float* prow = scratch + 2 * LDW;          // [2][PROW]
-  int* used = reinterpret_cast<int*>(prow + 2 * PROW);   // [LDW]
-  int* colof = used + LDW;                  // [LDW]: physical row -> the pivot column it served
+  int* colof = reinterpret_cast<int*>(prow + 2 * PROW);   // [LDW]: physical row -> the pivot column it served
   const int lane = tid & 31;
   float4 reg[PPT][4];
   int prt[PPT], pct[PPT];
@@ -221,7 +220,9 @@ __device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, i
       }
     }
   }
-  for (int i = tid; i < LDW; i += NT) { used[i] = 0; colof[i] = i; }
+  for (int i = tid; i < LDW; i += NT) colof[i] = i;
+  unsigned usedmask = 0u;   // bit u: row lane + 32 u has served as a pivot (kept identically by every warp)
+  static_assert(LDW <= 32 * 32, "used-row mask");
   for (int c = 0; c < k; ++c) {
     float* fc = fcol + (c & 1) * LDW;
     float* pw = prow + (c & 1) * PROW;
@@ -237,19 +238,23 @@ __device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, i
         }
       }
     __syncthreads();
-    unsigned long long best = 0ull;
-    for (int i = lane; i < k; i += 32)
-      if (!used[i]) {
-        const unsigned long long pk = (static_cast<unsigned long long>(__float_as_uint(fabsf(fc[i]))) << 32) |
-                                      static_cast<unsigned>(0x7fffffff - i);
-        best = pk > best ? pk : best;
-      }
+    // pivot = arg max |column c| over the rows not used yet, ties to the smallest row, NaN wins (it must propagate):
+    // every warp on its own -- each lane reduces its rows (lane, lane + 32, ...; their used flags live in a register
+    // mask), then two hardware warp reductions (max of the value bits, min of the rows that attain it)
+    unsigned bbits = 0u;
+    int brow = 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-      best = ob > best ? ob : best;
+    for (int u = 0; u < (LDW + 31) / 32; ++u) {
+      const int i = lane + 32 * u;
+      if (i < k && !((usedmask >> u) & 1u)) {
+        const unsigned b = __float_as_uint(fabsf(fc[i])) + 1u;   // + 1: a candidate always beats "none" (0); order kept
+        if (b > bbits) { bbits = b; brow = i; }
+      }
     }
-    const int pv = 0x7fffffff - static_cast<int>(static_cast<unsigned>(best & 0xffffffffull));
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, bbits);
+    const int pv = static_cast<int>(__reduce_min_sync(0xffffffffu, bbits == wmax ? static_cast<unsigned>(brow) : 0x7fffffffu));
+    if ((pv & 31) == lane) usedmask |= 1u << (pv >> 5);
+    const float inv = 1.f / fc[pv];
     // the pivot row, from its owners
 #pragma unroll
     for (int q = 0; q < PPT; ++q)
@@ -258,9 +263,8 @@ __device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, i
         const float4 x = a == 0 ? reg[q][0] : (a == 1 ? reg[q][1] : (a == 2 ? reg[q][2] : reg[q][3]));
         *reinterpret_cast<float4*>(pw + 4 * pct[q]) = x;
       }
+    if (tid == 0) colof[pv] = c;
     __syncthreads();
-    if (tid == 0) { used[pv] = 1; colof[pv] = c; }   // read again only after the next barrier
-    const float inv = 1.f / fc[pv];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       if (prt[q] < 0) continue;
@@ -271,13 +275,11 @@ __device__ __forceinline__ void gauss_jordan_reg(float* W, float* R, float* v, i
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const float f = a == 0 ? f4.x : (a == 1 ? f4.y : (a == 2 ? f4.z : f4.w));
-        if (4 * prt[q] + a == pv) {
-          reg[q][a] = pr;
-        } else {
-          float4 x = reg[q][a];
-          x.x = fmaf(-f, pr.x, x.x); x.y = fmaf(-f, pr.y, x.y); x.z = fmaf(-f, pr.z, x.z); x.w = fmaf(-f, pr.w, x.w);
-          reg[q][a] = x;
-        }
+        const bool piv = 4 * prt[q] + a == pv;
+        float4 x = reg[q][a];
+        x.x = piv ? pr.x : fmaf(-f, pr.x, x.x); x.y = piv ? pr.y : fmaf(-f, pr.y, x.y);
+        x.z = piv ? pr.z : fmaf(-f, pr.z, x.z); x.w = piv ? pr.w : fmaf(-f, pr.w, x.w);
+        reg[q][a] = x;
       }
     }
   }

@@ -35,10 +35,10 @@ def _unwrap(p):
     return p, args
 
 
-# measured on B200 at E = 1 (profiles/r01ao_launches_*_e1_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
+# measured on B200 at E = 1 (profiles/r01ap_launches_*_e1_pscan.csv, r01ah_talos_horizon_sweep.jsonl), microseconds:
 # n -> (sequential kernel per knot, parallel-scan combine per level, parallel-scan fixed part, its rollout per knot)
-_LQ_COST_US = {13: (8.9, 16.9, 28.0, 1.2), 61: (18.0, 102.0, 68.0, 2.7), 75: (30.5, 144.0, 97.0, 3.4),
-               81: (79.0, 171.0, 251.0, 4.1)}
+_LQ_COST_US = {13: (8.9, 15.3, 24.5, 1.2), 61: (18.0, 92.6, 64.0, 2.7), 75: (30.5, 131.0, 89.0, 3.4),
+               81: (79.0, 158.6, 230.0, 4.1)}
 
 
 def wrapper_lq_mode(limited_memory, n_env, n, N):
@@ -52,8 +52,8 @@ def wrapper_lq_mode(limited_memory, n_env, n, N):
     * ``limited_memory=False`` -> the scan scheduled in parallel over the horizon (one CTA per knot, log2 levels) when
       its modelled time  fixed + levels x waves x combine  beats  N x knot  of the sequential kernel, with the
       per-size constants measured at E = 1 (``_LQ_COST_US``; waves = ceil(n_env (N + 1) / 148)): single instances of
-      the SRBD model (tick 0.23 vs 0.28 ms) and of Talos (N = 25: LQ 1.28 vs 1.99 ms; N = 200: 3.7 vs 15.3 ms), long
-      horizons in general; Aliengo / Go2 at N = 25 (0.62 vs 0.45 ms) and every large batch stay on the sequential
+      the SRBD model (tick 0.18 vs 0.28 ms) and of Talos (N = 25: LQ 1.04 vs 1.99 ms; N = 200: 3.7 vs 15.3 ms), long
+      horizons in general; Aliengo / Go2 at N = 25 (0.56 vs 0.45 ms), H1 (0.77 vs 0.76 ms) and every large batch stay on the sequential
       kernel, where one CTA per environment already fills the GPU and the scan's ~9x FLOPs buy nothing.
 
     ``MPXB_LQ=scan`` in the environment restores the literal mapping (``LQ_SCAN``), ``MPXB_LQ=sequential`` forces the
