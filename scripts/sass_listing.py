@@ -1,5 +1,5 @@
 """SASS listings of the hot Go2 / H1 / SRBD kernels in mpx_b200/libmpxb.so (cuobjdump -sass), encodings stripped:
-    python scripts/sass_listing.py <tag>
+    python scripts/sass_listing.py <tag> [name-prefix,...]
 writes profiles/sass/<tag>_<kernel>.sass.gz (instruction text, one per line) and profiles/<tag>_sass_opcodes.txt
 (instruction count and opcode histogram per kernel -- FFMA share, LDS/LDG/LDL counts, no HMMA/UTCMMA expected: the
 path is FP32 CUDA-core work)."""
@@ -16,7 +16,14 @@ kernels = {
     "wb_trial3_quad": "_ZN4mpxb16wb_trial3_kernelILi14ELi18ELi4ELi64EEEvPKNS_7WbModelENS_7ModelIOENS_8TrialOutE",
     "srbd_linearize": "_ZN4mpxb21srbd_linearize_kernelENS_10SrbdParamsENS_7ModelIOENS_6LinOutE",
     "select_update": "_ZN4mpxb20select_update_kernelENS_10SelectArgsE",
+    "pscan_combine_81": "_ZN4mpxb20pscan_combine_kernelILi81ELi512EEEviiPKiNS_8PscanBufES3_",
+    "pscan_combine_13": "_ZN4mpxb20pscan_combine_kernelILi13ELi512EEEviiPKiNS_8PscanBufES3_",
+    "pscan_init_81_46": "_ZN4mpxb17pscan_init_kernelILi81ELi46ELi256EEEvNS_6LqArgsENS_8PscanBufE",
+    "pscan_gains_81_46": "_ZN4mpxb18pscan_gains_kernelILi81ELi46ELi256EEEvNS_6LqArgsENS_8PscanBufE",
 }
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None   # optional: comma-separated name prefixes
+if only:
+    kernels = {k: v for k, v in kernels.items() if any(k.startswith(o) for o in only)}
 os.makedirs(os.path.join(root, "profiles", "sass"), exist_ok=True)
 rep = []
 for name, sym in kernels.items():
