@@ -273,6 +273,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION / INFO print to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("MPXB_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     robot, desc = WORKLOADS[args.workload]
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
