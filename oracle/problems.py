@@ -82,24 +82,26 @@ def rpy_to_quat(r, p, y):
                      cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
 
 
-def synthetic_inputs(problem, n_env, seed=0, cold_start=False):
+def synthetic_inputs(problem, n_env, seed=0, cold_start=False, scale=1.0):
     """per-env random robot state + command -> (reference, parameter, x0, X0, U0, V0) float64 numpy.
 
     Draw order per env: height, rpy, q, v_lin, omega, dq, command, gait phase.  ``cold_start`` gives the exact
-    identity-quaternion / zero-velocity state of ``reset`` (the safe-norm discontinuity case).
+    identity-quaternion / zero-velocity state of ``reset`` (the safe-norm discontinuity case).  ``scale`` multiplies
+    the ranges of the random robot state (not of the command): states far from the nominal stance, where the line
+    search has to cut the step.
     """
     cfg = problem.config
     rng = np.random.default_rng(seed)
     N, nc = cfg.N, cfg.n_contact
     out = {k: [] for k in ("reference", "parameter", "x0", "X0", "U0", "V0")}
     for _ in range(n_env):
-        dz = rng.uniform(-0.02, 0.02)
-        rpy = rng.uniform(-0.1, 0.1, 3)
+        dz = scale * rng.uniform(-0.02, 0.02)
+        rpy = scale * rng.uniform(-0.1, 0.1, 3)
         nj = 0 if problem.is_srbd else cfg.n_joints
-        dq_pos = rng.uniform(-0.05, 0.05, cfg.n_joints)
-        v_lin = rng.uniform(-0.2, 0.2, 3)
-        omega = rng.uniform(-0.2, 0.2, 3)
-        dq = rng.uniform(-0.5, 0.5, cfg.n_joints)
+        dq_pos = scale * rng.uniform(-0.05, 0.05, cfg.n_joints)
+        v_lin = scale * rng.uniform(-0.2, 0.2, 3)
+        omega = scale * rng.uniform(-0.2, 0.2, 3)
+        dq = scale * rng.uniform(-0.5, 0.5, cfg.n_joints)
         cmd = np.array([rng.uniform(-0.2, 0.5), rng.uniform(-0.1, 0.1), 0, 0, 0, rng.uniform(-0.3, 0.3),
                         cfg.robot_height])
         phase = rng.uniform(0, 1)

@@ -30,35 +30,18 @@ def _run(solver, inp, W=None):
 
 
 @pytest.mark.parametrize("eager", [True, False])
-@pytest.mark.parametrize("limited_memory", [True, False])
-@pytest.mark.parametrize("cold", [False, True])
-def test_srbd_step_matches_oracle(problem, limited_memory, cold, eager):
-    from mpx_b200.primal_dual_ilqr.optimizers import MpcSolver
-    E = 3
-    inp = synthetic_inputs(problem, E, seed=11, cold_start=cold)
-    solver = MpcSolver(cfg, E, limited_memory=limited_memory, eager_line_search=eager)
-    X, U, V = _run(solver, inp)
-    for e in range(E):
-        det = {}
-        Xo, Uo, Vo = problem.mpc(limited_memory, inp["reference"][e], inp["parameter"][e], inp["x0"][e],
-                                 inp["X0"][e], inp["U0"][e], inp["V0"][e], detail=det)
-        # linearisation / quadratisation
-        for nm in ("A", "B", "Q", "R", "M", "q", "r"):
-            assert _rel(solver.view(nm)[e].cpu().numpy(), det[nm].numpy()) < REL_TOL, nm
-        assert _rel(solver.view("c")[e].cpu().numpy(), det["c"].numpy()) < REL_TOL
-        assert abs(float(solver.view("g")[e]) - float(det["g"])) / abs(float(det["g"])) < REL_TOL
-        # gains, value function, search direction, multipliers
-        for nm in ("K", "k", "P", "p", "dX", "dU", "dV"):
-            assert _rel(solver.view(nm)[e].cpu().numpy(), det[nm].numpy()) < REL_TOL, nm
-        # line search: same merit data, same accepted step
-        npts = 11 if (eager or det["alpha_index"] > 0) else 1  # lazy: points 1..10 only if alpha = 1 is rejected
-        assert _rel(solver.view("ls_theta")[e, :npts].cpu().numpy(), det["theta"].numpy()[:npts]) < 1e-3
-        assert _rel(solver.view("ls_phi")[e, :npts].cpu().numpy(), det["phi"].numpy()[:npts]) < REL_TOL
-        assert int(solver.alpha_index[e]) == det["alpha_index"]
-        assert _rel(X[e].cpu().numpy(), Xo.numpy()) < REL_TOL
-        assert _rel(U[e].cpu().numpy(), Uo.numpy()) < REL_TOL
-        assert _rel(V[e].cpu().numpy(), Vo.numpy()) < REL_TOL
-        assert int(solver.status[e]) == 0 and int(solver.iters[e]) == 1
+@pytest.mark.parametrize("lq", ["sequential", "scan_parallel", "scan_serial"])
+@pytest.mark.parametrize("case", ["warm", "second", "cold", "far"])
+def test_srbd_step_matches_golden(case, lq, eager):
+    """One optimizers.mpc call of the SRBD model (config 1) against tests/golden/srbd_<case>.npz: every intermediate,
+    the accepted step and X, U, V, block by block (tests/parity.py), for the sequential LQ kernel and both schedules of
+    the associative scan (mpc_wrapper_srbd.py:68 binds limited_memory=False)."""
+    from mpx_b200 import _lib
+    from golden_check import load, solve, check_step
+    g = load("srbd", case)
+    mode = {"sequential": _lib.LQ_SEQUENTIAL, "scan_parallel": _lib.LQ_SCAN_PARALLEL, "scan_serial": _lib.LQ_SCAN_SERIAL}[lq]
+    solver, X, U, V = solve(cfg, g, mode, eager)
+    check_step(cfg, g, solver, X, U, V, "" if lq == "sequential" else "_scan", eager)
 
 
 def test_srbd_per_env_W_equals_shared(problem):
