@@ -1,5 +1,6 @@
 """Shared checker of the golden-fixture parity tests (TEST INFRASTRUCTURE): load a fixture, run one mpc call through
 the C ABI, compare every intermediate and output block by block (tests/parity.py)."""
+import json
 import os
 
 import numpy as np
@@ -8,15 +9,38 @@ import torch
 import parity
 
 REL_TOL = 1e-4
+# no scan-mode budget, however large, relaxes a check beyond 5 %: the associative scan in float32 on whole-body LQ data
+# is unstable enough that equivalent float32 evaluations of the reference algorithm differ by O(1) (parity;
+# tests/golden/budgets_*.json), and a budget of that size would make the comparison vacuous
+TOL_CAP = 5e-2
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LIN = ("A", "B", "Q", "R", "M", "q", "r", "c")
 LQ = ("K", "k", "P", "p", "dX", "dU", "dV")
 
 
+class Fixture:
+    """A golden fixture (tests/golden/<robot>_<case>.npz) with its FP32 budgets (tests/golden/budgets_<robot>.json,
+    made by tests/golden/make_budgets.py): fx["A"] reads an array, fx.budget("A", e) the budget of environment e."""
+
+    def __init__(self, robot, case):
+        path = os.path.join(GOLDEN, f"{robot}_{case}.npz")
+        assert os.path.exists(path), f"{path} missing (run tests/golden/make_golden.py)"
+        self.npz = np.load(path)
+        bpath = os.path.join(GOLDEN, f"budgets_{robot}.json")
+        assert os.path.exists(bpath), f"{bpath} missing (run tests/golden/make_budgets.py)"
+        with open(bpath) as f:
+            self.budgets = json.load(f)[f"{robot}_{case}"]
+        self.files = self.npz.files
+
+    def __getitem__(self, key):
+        return self.npz[key]
+
+    def budget(self, key, e):
+        return float(self.budgets[key][e])
+
+
 def load(robot, case):
-    path = os.path.join(GOLDEN, f"{robot}_{case}.npz")
-    assert os.path.exists(path), f"{path} missing (run tests/golden/make_golden.py)"
-    return np.load(path)
+    return Fixture(robot, case)
 
 
 def solve(cfg, g, lq_mode, eager=True):
@@ -35,7 +59,7 @@ def check_step(cfg, g, solver, X, U, V, sfx, eager):
     E = g["x0"].shape[0]
     fails = []
     for e in range(E):
-        tol = lambda key: max(REL_TOL, 4 * float(g["budget_" + key][e]))
+        tol = lambda key: max(REL_TOL, min(4 * g.budget(key, e), TOL_CAP if key.endswith("_scan") else 1.0))
         for nm in LIN:
             err = parity.block_rel_err(nm, solver.view(nm)[e].cpu().numpy(), g[nm][e], segs,
                                        magnitude=g["X0"][e] if nm == "c" else None)
