@@ -16,8 +16,11 @@
  *   - calls are asynchronous on `stream`, allocate nothing, never synchronise and can be captured in a CUDA graph;
  *   - return value: 0 on success, negative MPXB_E* for ARGUMENT errors only.  Numerical failure is reported
  *     in-band exactly like the reference (NaNs in the outputs, mpc_wrapper.py:96,280) plus status[e] != 0.
- *   - no global mutable state; a model handle is immutable after creation and may be used from several
- *     streams of its device concurrently as long as each call has its own workspace.
+ *   - no global mutable state; a model handle is immutable after creation (options are set before the first
+ *     step) and may be used from several streams of its device concurrently as long as each call has its own
+ *     workspace.  A handle belongs to the device that was current at mpxb_model_create; every entry point
+ *     switches to that device for its launches and restores the caller's current device.
+ *   - `workspace` must be 256-byte aligned.
  */
 #ifndef MPXB_H_
 #define MPXB_H_
@@ -115,9 +118,18 @@ void mpxb_model_destroy(mpxb_model* model);
  * MPXB_OPT_LINE_SEARCH (default MPXB_LS_FILTER): MPXB_LS_FILTER is parallel_filter_line_search, the search the
  * reference's mpc runs (optimizers.py:468-578, 670-681); MPXB_LS_MERIT is parallel_line_search on the augmented
  * Lagrangian merit g + sum((V + rho/2 c) c) with merit_rho / slope (optimizers.py:185-217, 295-354), the call the
- * reference keeps commented out at optimizers.py:637-669. */
-enum { MPXB_OPT_EAGER_LINE_SEARCH = 1, MPXB_OPT_LINE_SEARCH = 2 };
+ * reference keeps commented out at optimizers.py:637-669.
+ * MPXB_OPT_COST_STRUCTURE (default MPXB_COST_DENSE): MPXB_COST_DIAGONAL_W is the caller's promise that the weight
+ * matrix W passed to mpxb_mpc_step is DIAGONAL (every shipped config: block_diag of diag(...), config_*.py).  The
+ * Gauss-Newton blocks of the whole-body objectives (objectives.py:127-202, 252-323, 378-450) are then Q_t = diag + a
+ * 4x4 quaternion block (+ 3x3 friction-cone blocks), R_t = diag, M_t = 0, and with limited_memory = True
+ * (MPXB_LQ_SEQUENTIAL) the solve runs the structured kernels (csrc/lq3.cuh): same recursion, structural zeros never
+ * multiplied, LQ data in packed blocks moved by bulk asynchronous copies.  X, U, V agree with the dense path to
+ * rounding.  The dense views "A".."p" are then filled by mpxb_workspace_expand.  Ignored for MPXB_KIND_SRBD and the
+ * scan modes.  A non-diagonal W with this option set gives wrong results (the off-diagonal entries are never read). */
+enum { MPXB_OPT_EAGER_LINE_SEARCH = 1, MPXB_OPT_LINE_SEARCH = 2, MPXB_OPT_COST_STRUCTURE = 3 };
 enum { MPXB_LS_FILTER = 0, MPXB_LS_MERIT = 1 };
+enum { MPXB_COST_DENSE = 0, MPXB_COST_DIAGONAL_W = 1 };
 int mpxb_model_set_option(mpxb_model* model, int option, int value);
 
 /* Bytes of device scratch one mpxb_mpc_step call with E environments needs. */
@@ -145,6 +157,9 @@ int mpxb_mpc_step(const mpxb_model* model, void* stream /* cudaStream_t */, int 
  * "dX","dU","dV","ls_theta","ls_phi","g"}.  Returns a device pointer inside `workspace` or NULL. */
 const float* mpxb_workspace_view(const mpxb_model* model, int E, int lq_mode, void* workspace, const char* name,
                                  size_t* count);
+/* With MPXB_COST_DIAGONAL_W the last call kept A, B, Q, R, M, q, r, K, k, P, p in packed form; this launches (stream-
+ * ordered) the kernel that writes them out densely where mpxb_workspace_view points.  A no-op for the dense path. */
+int mpxb_workspace_expand(const mpxb_model* model, void* stream, int E, int lq_mode, void* workspace);
 
 /* Warm-start shift / NaN guard / command extraction of update_and_extract_helper
  * (mpc_wrapper.py:79-98, 261-282; mpc_wrapper_srbd.py:135-139), batched over E, stream-ordered.

@@ -12,6 +12,8 @@ MAX_BODY, MAX_DOF, MAX_CONTACT = 32, 32, 8
 KIND_SRBD, KIND_QUAD_WB, KIND_H1_WB, KIND_TALOS_WB = 0, 1, 2, 3
 OPT_EAGER_LINE_SEARCH = 1
 OPT_LINE_SEARCH = 2
+OPT_COST_STRUCTURE = 3
+COST_DENSE, COST_DIAGONAL_W = 0, 1
 LS_FILTER, LS_MERIT = 0, 1
 LQ_SEQUENTIAL, LQ_SCAN, LQ_SCAN_SERIAL, LQ_SCAN_PARALLEL = 0, 1, 2, 3
 ERRORS = {0: "ok", -1: "MPXB_EINVAL", -2: "MPXB_EUNSUPPORTED", -3: "MPXB_EWORKSPACE", -4: "MPXB_ECUDA"}
@@ -70,6 +72,8 @@ def lib():
     L.mpxb_mpc_step.restype = i32
     L.mpxb_workspace_view.argtypes = [vp, i32, i32, vp, C.c_char_p, C.POINTER(sz)]
     L.mpxb_workspace_view.restype = vp
+    L.mpxb_workspace_expand.argtypes = [vp, vp, i32, i32, vp]
+    L.mpxb_workspace_expand.restype = i32
     L.mpxb_shift_extract.argtypes = [vp, vp, i32, i32] + [f32p] * 11
     L.mpxb_shift_extract.restype = i32
     L.mpxb_tvlqr.argtypes = [vp, i32, i32, i32, i32, i32] + [f32p] * 16 + [vp]

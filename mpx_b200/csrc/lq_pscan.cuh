@@ -653,6 +653,17 @@ __global__ void __launch_bounds__(NT) pscan_rollout_kernel(LqArgs a, int arena) 
   lq_rollout_stream<n, m, NT>(a, e, tid, smem, acols, arena);
 }
 
+// > 48 KB of dynamic shared memory is a per-device function attribute: set at model creation (mpxb_model_create) and by
+// the stand-alone mpxb_tvlqr, never inside a launch sequence that may be under stream capture
+template <int n, int m> cudaError_t configure_lq_pscan() {
+  constexpr int NT = 256, NTC = 512;
+  cudaError_t err = cudaFuncSetAttribute(pscan_init_kernel<n, m, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanInitSmem<n, m>::bytes));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(pscan_combine_kernel<n, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanCombineSmem<n>::bytes));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(pscan_gains_kernel<n, m, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanGainSmem<n, m>::bytes));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(pscan_rollout_kernel<n, m, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
+  return err;
+}
+
 template <int n, int m> cudaError_t launch_lq_pscan(const LqArgs& a, float* ws, cudaStream_t st) {
   // threads per CTA: 256 / 512 also for the small sizes (two-warp CTAs measured slower for SRBD, tick 0.26 vs 0.23 ms:
   // the kernels are bound by load and barrier latency, which more warps overlap)
@@ -664,17 +675,6 @@ template <int n, int m> cudaError_t launch_lq_pscan(const LqArgs& a, float* ws, 
   auto k_gain = pscan_gains_kernel<n, m, NT>;
   auto k_roll = pscan_rollout_kernel<n, m, NT>;
   const size_t roll_bytes = lq_rt_bytes<n, m>(a.nzc);
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanInitSmem<n, m>::bytes));
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_comb, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanCombineSmem<n>::bytes));
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_gain, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PscanGainSmem<n, m>::bytes));
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(k_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
-    if (err != cudaSuccess) return err;
-    configured[dev] = true;
-  }
   const size_t cnt = size_t(a.E) * (a.N + 1);
   PscanBuf buf[2] = {pscan_buf(ws, 0, cnt, n), pscan_buf(ws, 1, cnt, n)};
   const dim3 grid(a.N + 1, a.E);

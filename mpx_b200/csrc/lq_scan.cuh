@@ -277,17 +277,12 @@ __global__ void __launch_bounds__(NT) lq_scan_kernel(LqArgs a) {
   lq_rollout_dual<n, m, NT>(a, e, tid, sv, sx, sh);
 }
 
+template <int n, int m> cudaError_t configure_lq_scan() {
+  return cudaFuncSetAttribute(lq_scan_kernel<n, m, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LqScanSmem<n, m>::bytes));
+}
 template <int n, int m> cudaError_t launch_lq_scan(const LqArgs& a, cudaStream_t st) {
   constexpr int NT = 256;
   auto kern = lq_scan_kernel<n, m, NT>;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LqScanSmem<n, m>::bytes));
-    if (err != cudaSuccess) return err;
-    configured[dev] = true;
-  }
   kern<<<a.E, NT, LqScanSmem<n, m>::bytes, st>>>(a);
   return cudaGetLastError();
 }

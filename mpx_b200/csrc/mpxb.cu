@@ -18,6 +18,7 @@
 #include "wb_launch.h"
 #include "lq_scan.cuh"
 #include "lq_pscan.cuh"
+#include "lq3.cuh"
 #include "refgen.cuh"
 
 using namespace mpxb;
@@ -34,8 +35,22 @@ struct mpxb_model {
   WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
   int eager_line_search;  // 1: evaluate all 11 trial points every call (default 0: lazy, same result)
   int merit_line_search;  // 1: merit-function line search instead of the filter
+  int structured;         // MPXB_OPT_COST_STRUCTURE: 1 = W is diagonal (checked by the host) -> structured LQ path
+  bool s3_ok;             // the structured kernels are compiled for this model's dimensions
+  Lq3Layout s3;
   WbModel wb_host;
   int device;
+};
+
+// Entry points may be called with another device current (one handle per GPU, several GPUs per process): launch on
+// the model's device and restore the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 namespace {
@@ -43,16 +58,51 @@ namespace {
 template <int n, int m> cudaError_t launch_lq_seq(const LqArgs& a, cudaStream_t st) {
   constexpr int NT = 256;
   auto kern = lq_seq_kernel<n, m, NT>;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
-    if (err != cudaSuccess) return err;
-    configured[dev] = true;
-  }
   kern<<<a.E, NT, lq_rt_bytes<n, m>(a.nzc), st>>>(a);
   return cudaGetLastError();
+}
+// > 48 KB of dynamic shared memory is a per-device function attribute.  It is set for every LQ kernel of a problem
+// size at model creation (and by the stand-alone mpxb_tvlqr), never inside a launch sequence: the library keeps no
+// mutable global state and a captured launch sequence contains launches only.
+template <int n, int m> cudaError_t configure_lq() {
+  cudaError_t err = cudaFuncSetAttribute(lq_seq_kernel<n, m, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
+  if (err == cudaSuccess) err = configure_lq_scan<n, m>();
+  if (err == cudaSuccess) err = configure_lq_pscan<n, m>();
+  return err;
+}
+int configure_lq_dispatch(int n, int m) {
+#define MPXB_LQ_CASE(NN, MM) if (n == NN && m == MM) return configure_lq<NN, MM>() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+  MPXB_LQ_CASE(13, 12)
+  MPXB_LQ_CASE(61, 12)
+  MPXB_LQ_CASE(75, 19)
+  MPXB_LQ_CASE(81, 46)
+  MPXB_LQ_CASE(2, 1)
+  MPXB_LQ_CASE(4, 1)
+  MPXB_LQ_CASE(8, 2)
+#undef MPXB_LQ_CASE
+  return MPXB_EUNSUPPORTED;
+}
+
+// structured whole-body LQ kernel (lq3.cuh): quadrupeds, H1, Talos
+template <int NH, int NTL, int M, int NCONE, int NT> cudaError_t launch_lq3(const Lq3Args& a, cudaStream_t st) {
+  using D = Lq3Dims<NH, NTL, M, NCONE>;
+  auto kern = lq3_kernel<NH, NTL, M, NCONE, NT>;
+  if (a.E == 0)  // configure only (mpxb_model_create)
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Lq3Smem<D>::bytes));
+  kern<<<a.E, NT, Lq3Smem<D>::bytes, st>>>(a);
+  return cudaGetLastError();
+}
+bool lq3_supported(const Lq3Layout& s) {
+  return (s.nh == 37 && s.ntl == 24 && s.m == 12 && s.ncone == 4) || (s.nh == 51 && s.ntl == 24 && s.m == 19 && s.ncone == 0) ||
+         (s.nh == 57 && s.ntl == 24 && s.m == 46 && s.ncone == 0);
+}
+int dispatch_lq3(const Lq3Layout& s, const Lq3Args& a, cudaStream_t st) {
+  cudaError_t err = cudaErrorInvalidValue;
+  if (s.nh == 37 && s.m == 12) err = launch_lq3<37, 24, 12, 4, 64>(a, st);
+  else if (s.nh == 51 && s.m == 19) err = launch_lq3<51, 24, 19, 0, 64>(a, st);
+  else if (s.nh == 57 && s.m == 46) err = launch_lq3<57, 24, 46, 0, 64>(a, st);
+  else return MPXB_EUNSUPPORTED;
+  return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
 int dispatch_lq_seq(int n, int m, const LqArgs& a, cudaStream_t st) {
@@ -104,6 +154,13 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   mdl->prof = nullptr;
   mdl->eager_line_search = 0;
   mdl->merit_line_search = 0;
+  mdl->structured = 0;
+  mdl->s3_ok = false;
+  if (d->kind != MPXB_KIND_SRBD) {
+    const int nh = 13 + 2 * d->n_joints;
+    mdl->s3 = lq3_layout(nh, d->n - nh, d->m, d->kind == MPXB_KIND_QUAD_WB ? d->n_contact : 0);
+    mdl->s3_ok = d->n > nh && lq3_supported(mdl->s3);
+  }
   cudaGetDevice(&mdl->device);
   if (d->kind == MPXB_KIND_SRBD) {
     if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
@@ -124,6 +181,14 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
       return MPXB_ECUDA;
     }
   }
+  // per-device function attributes of every kernel this model can launch
+  int rc = configure_lq_dispatch(d->n, d->m);
+  if (rc == MPXB_OK && d->kind != MPXB_KIND_SRBD) rc = wb_launch_configure(mdl->wb_host);
+  if (rc == MPXB_OK && mdl->s3_ok) {
+    Lq3Args none{};
+    rc = dispatch_lq3(mdl->s3, none, nullptr);
+  }
+  if (rc != MPXB_OK) { mpxb_model_destroy(mdl); return rc; }
   *out = mdl;
   return MPXB_OK;
 }
@@ -131,6 +196,11 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
 int mpxb_model_set_option(mpxb_model* m, int option, int value) {
   if (!m) return MPXB_EINVAL;
   if (option == MPXB_OPT_EAGER_LINE_SEARCH) { m->eager_line_search = value ? 1 : 0; return MPXB_OK; }
+  if (option == MPXB_OPT_COST_STRUCTURE) {
+    if (value != MPXB_COST_DENSE && value != MPXB_COST_DIAGONAL_W) return MPXB_EINVAL;
+    m->structured = (value == MPXB_COST_DIAGONAL_W);
+    return MPXB_OK;
+  }
   if (option == MPXB_OPT_LINE_SEARCH) {
     if (value != MPXB_LS_FILTER && value != MPXB_LS_MERIT) return MPXB_EINVAL;
     m->merit_line_search = (value == MPXB_LS_MERIT);
@@ -166,7 +236,11 @@ static int dispatch_lq(int lq_mode, int n, int m, const LqArgs& la, float* scan_
 static WsLayout layout_of(const mpxb_model* mdl, int E, int lq_mode) {
   const mpxb_model_desc& d = mdl->desc;
   size_t scan = lq_scan_ws_floats(lq_mode, E, d.N, d.n);
-  return make_layout(E, d.N, d.n, d.m, scan);
+  return make_layout(E, d.N, d.n, d.m, scan, mdl->s3_ok ? &mdl->s3 : nullptr);
+}
+// the structured path serves limited_memory=True (tvlqr + rollout) once the host has vouched for a diagonal W
+static bool use_structured(const mpxb_model* mdl, int lq_mode) {
+  return mdl->structured && mdl->s3_ok && lq_mode == MPXB_LQ_SEQUENTIAL;
 }
 
 size_t mpxb_workspace_bytes(const mpxb_model* mdl, int E, int lq_mode) {
@@ -183,7 +257,11 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
   if (E <= 0 || max_iter <= 0) return MPXB_EINVAL;
   if (!lq_mode_valid(lq_mode, E)) return MPXB_EINVAL;
   if (X == X_in || U == U_in || V == V_in) return MPXB_EINVAL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return MPXB_EINVAL;  // bulk copies need 16-byte aligned blocks
+  DeviceGuard guard(mdl->device);
   const mpxb_model_desc& d = mdl->desc;
+  const bool structured = use_structured(mdl, lq_mode);
+  const Lq3Layout& s3 = mdl->s3;
   const WsLayout L = layout_of(mdl, E, lq_mode);
   if (workspace_bytes < L.total * sizeof(float)) return MPXB_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -200,7 +278,13 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     float* Un = to_user ? U : ws + L.Ut;
     float* Vn = to_user ? V : ws + L.Vt;
     ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
-    LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost};
+    LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost,
+              n, m, 0, nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (structured) {
+      lo.A = ws + L.Ac; lo.B = ws + L.Bc; lo.ldA = s3.LH; lo.ldB = s3.LMB; lo.compact = 1; lo.PK = ws + L.PK;
+      lo.pks = s3.PKS; lo.oQd = s3.oQd; lo.oq = s3.oq; lo.oc = s3.oc; lo.oQq = s3.oQq; lo.oQc = s3.oQc; lo.oRd = s3.oRd;
+      lo.oR = s3.oR;
+    }
     int32_t* need = reinterpret_cast<int32_t*>(ws + L.need);
     TrialOut to{ws + L.dX, ws + L.dU, ws + L.ls_theta, ws + L.ls_phi, ws + L.c, ws + L.cost, ws + L.slope,
                 ws + L.theta_k, ws + L.phi_k, need, 0, NALPHA, mdl->merit_line_search, ws + L.dV, ws + L.ls_vc,
@@ -225,7 +309,14 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
               ws + L.K, ws + L.k, ws + L.P, ws + L.p, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.slope, done,
               // whole-body models: the foot / GRF tail of the state never enters f, so those columns of A are zero
               d.kind == MPXB_KIND_SRBD ? 0 : 13 + 2 * d.n_joints};
-    int rc = dispatch_lq(lq_mode, n, m, la, ws + L.scan, st);
+    int rc;
+    if (structured) {
+      Lq3Args l3{E, N, ws + L.Ac, ws + L.Bc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc, ws + L.dX, ws + L.dU, ws + L.dV,
+                 ws + L.slope, done};
+      rc = dispatch_lq3(s3, l3, st);
+    } else {
+      rc = dispatch_lq(lq_mode, n, m, la, ws + L.scan, st);
+    }
     if (rc != MPXB_OK) return rc;
     if (pev) cudaEventRecord(pev[2], st);
     // K3: the 11 trial points.  Lazy (default): alpha = 1 first; the ten smaller steps only for the environments
@@ -282,10 +373,23 @@ const float* mpxb_workspace_view(const mpxb_model* mdl, int E, int lq_mode, void
   return nullptr;
 }
 
+int mpxb_workspace_expand(const mpxb_model* mdl, void* stream, int E, int lq_mode, void* workspace) {
+  if (!mdl || !workspace || E <= 0) return MPXB_EINVAL;
+  if (!use_structured(mdl, lq_mode)) return MPXB_OK;  // the dense path keeps the dense arrays up to date itself
+  DeviceGuard guard(mdl->device);
+  const WsLayout L = layout_of(mdl, E, lq_mode);
+  float* ws = static_cast<float*>(workspace);
+  ExpandArgs a{E, mdl->desc.N, mdl->s3, ws + L.Ac, ws + L.Bc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc,
+               ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.K, ws + L.k, ws + L.P, ws + L.p};
+  lq3_expand_kernel<<<E * (mdl->desc.N + 1), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
+}
+
 int mpxb_shift_extract(const mpxb_model* mdl, void* stream, int E, int shift, const float* X, const float* U,
                        const float* V, const float* x0, const float* u_ref, float* X0, float* U0, float* V0,
                        float* tau, float* q, float* dq) {
   if (!mdl || !X || !U || !V || !x0 || !u_ref || !X0 || !U0 || !V0 || E <= 0 || shift < 0) return MPXB_EINVAL;
+  DeviceGuard guard(mdl->device);
   const mpxb_model_desc& d = mdl->desc;
   const int wb = d.kind != MPXB_KIND_SRBD;
   shift_extract_kernel<<<E, 128, 0, static_cast<cudaStream_t>(stream)>>>(E, d.N, d.n, d.m, d.n_joints, shift, wb, X, U,
@@ -299,6 +403,7 @@ int mpxb_whole_body_interface(const mpxb_model* mdl, void* stream, int E, const 
   if (!mdl || !Kp || !Kd || !qpos || !qvel || !grf || !foot_ref || !foot_ref_dot || !contact || !tau || E <= 0)
     return MPXB_EINVAL;
   if (mdl->desc.kind != MPXB_KIND_QUAD_WB) return MPXB_EINVAL;
+  DeviceGuard guard(mdl->device);
   WbiArgs a{E, Kp, Kd, qpos, qvel, grf, foot_ref, foot_ref_dot, contact, tau, J};
   return wb_quad_interface(mdl->wb_host, mdl->wb_dev, a, static_cast<cudaStream_t>(stream));
 }
@@ -306,6 +411,7 @@ int mpxb_whole_body_interface(const mpxb_model* mdl, void* stream, int E, const 
 int mpxb_wb_foot_positions(const mpxb_model* mdl, void* stream, int E, const float* qpos, float* feet) {
   if (!mdl || !qpos || !feet || E <= 0) return MPXB_EINVAL;
   if (mdl->desc.kind == MPXB_KIND_SRBD) return MPXB_EINVAL;
+  DeviceGuard guard(mdl->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const WbModel& h = mdl->wb_host;
   const int nt = 64, nb = (E + nt - 1) / nt;
@@ -323,6 +429,7 @@ int mpxb_reference_generator(const mpxb_model* mdl, void* stream, int E, const m
   const mpxb_model_desc& d = mdl->desc;
   if (g->use_terrain_estimation && d.n_contact != 4) return MPXB_EINVAL;
   if (foot_stride < 3 * d.n_contact || d.n_contact > MPXB_MAX_CONTACT) return MPXB_EINVAL;
+  DeviceGuard guard(mdl->device);
   RefGenArgs a;
   a.E = E; a.N = d.N; a.nc = d.n_contact; a.srbd = d.kind == MPXB_KIND_SRBD; a.nj = a.srbd ? 0 : d.n_joints; a.n = d.n;
   a.use_terrain = g->use_terrain_estimation; a.advance_first = g->advance_timer_first;
@@ -390,6 +497,8 @@ int mpxb_tvlqr(void* stream, int E, int N, int n, int m, int lq_mode, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (E <= 0 || N <= 0 || !lq_mode_valid(lq_mode, E)) return MPXB_EINVAL;
   if (lq_mode != MPXB_LQ_SEQUENTIAL && !scan_ws) return MPXB_EINVAL;
+  int rc = configure_lq_dispatch(n, m);
+  if (rc != MPXB_OK) return rc;
   return dispatch_lq(lq_mode, n, m, la, static_cast<float*>(scan_ws), st);
 }
 
@@ -419,7 +528,7 @@ double mpxb_fp32_peak_tflops(void* stream, int iters) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int blocks = sms * 8, threads = 256;
   float* out = nullptr;
-  if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return MPXB_ECUDA;
+  if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return 0.0;  // "no measurement", never an error code as a rate
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);

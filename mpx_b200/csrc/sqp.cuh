@@ -5,6 +5,7 @@
 #include "model_io.cuh"
 #include <cuda_runtime.h>
 #include "common.cuh"
+#include "lq3.cuh"
 
 namespace mpxb {
 
@@ -12,12 +13,14 @@ namespace mpxb {
 // Offsets (in floats) of each per-batch array inside the caller's workspace.
 struct WsLayout {
   size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
-      done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, th_part, ph_part, vc_part, need_count, total;
+      done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, th_part, ph_part, vc_part, need_count,
+      // structured path (lq3.cuh): compact A / B, packed knot blocks, compact K / P, packed p | k
+      Ac, Bc, PK, Kc, Pc, OKc, total;
 };
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
 
-inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
+inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats, const Lq3Layout* s3 = nullptr) {
   WsLayout L;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o = align64(o + cnt); return r; };
@@ -59,6 +62,15 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats) {
   L.ph_part = take(e * NALPHA * (N + 1));
   L.vc_part = take(e * NALPHA * (N + 1));
   L.need_count = take(1);  // int32
+  L.Ac = L.Bc = L.PK = L.Kc = L.Pc = L.OKc = 0;
+  if (s3) {
+    L.Ac = take(e * N * s3->szA);
+    L.Bc = take(e * N * s3->szB);
+    L.PK = take(e * (N + 1) * s3->PKS);
+    L.Kc = take(e * N * s3->szK);
+    L.Pc = take(e * (N + 1) * s3->szP);
+    L.OKc = take(e * (N + 1) * s3->OKS);
+  }
   L.total = o;
   return L;
 }
@@ -198,6 +210,76 @@ __global__ void shift_extract_kernel(int E, int N, int n, int m, int nj, int shi
     const int t = int(i / m), j = int(i % m);
     const int ts = min(t + shift, N - 1);
     U0e[i] = Ue[size_t(ts) * m + j];
+  }
+}
+
+// Debug / parity views of the structured path: rebuild the dense arrays the reference's LQ solver works with
+// (A, B, Q, R, M, q, r, K, k, P, p) from the compact ones.  One CTA per (environment, knot).
+struct ExpandArgs {
+  int E, N;
+  Lq3Layout s;
+  const float *Ac, *Bc, *PK, *Kc, *Pc, *OKc;
+  float *A, *B, *Q, *R, *M, *q, *r, *K, *k, *P, *p;
+};
+__global__ void lq3_expand_kernel(ExpandArgs a) {
+  const int e = blockIdx.x / (a.N + 1), t = blockIdx.x - e * (a.N + 1);
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const Lq3Layout& s = a.s;
+  const int n = s.n, m = s.m, nh = s.nh, N = a.N;
+  const float* pk = a.PK + (size_t(e) * (N + 1) + t) * s.PKS;
+  const float* ok = a.OKc + (size_t(e) * (N + 1) + t) * s.OKS;
+  const float* Pc = a.Pc + (size_t(e) * (N + 1) + t) * s.szP;
+  // Q_t structure: diag + quaternion block + cone blocks
+  auto qent = [&](int i, int j) -> float {
+    float v = (i == j) ? pk[s.oQd + i] : 0.f;
+    if (i >= 3 && i < 7 && j >= 3 && j < 7) v = pk[s.oQq + (i - 3) * 4 + (j - 3)];
+    if (s.ncone > 0 && i >= s.cone0 && j >= s.cone0 && (i - s.cone0) / 3 == (j - s.cone0) / 3) {
+      const int blk = (i - s.cone0) / 3;
+      v += pk[s.oQc + 9 * blk + 3 * (i - s.cone0 - 3 * blk) + (j - s.cone0 - 3 * blk)];
+    }
+    return v;
+  };
+  float* Q = a.Q + (size_t(e) * (N + 1) + t) * n * n;
+  float* P = a.P + (size_t(e) * (N + 1) + t) * n * n;
+  for (int idx = tid; idx < n * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    const float qv = qent(i, j);
+    Q[idx] = qv;
+    P[idx] = (i < nh && j < nh) ? Pc[i * s.LH + j] : ((i >= nh && j >= nh) ? qv : 0.f);
+  }
+  for (int i = tid; i < n; i += NT) {
+    a.q[(size_t(e) * (N + 1) + t) * n + i] = pk[s.oq + i];
+    a.p[(size_t(e) * (N + 1) + t) * n + i] = (i < nh) ? ok[i] : pk[s.oq + i];
+  }
+  if (t == N) return;
+  const float* Ac = a.Ac + (size_t(e) * N + t) * s.szA;
+  const float* Bc = a.Bc + (size_t(e) * N + t) * s.szB;
+  const float* Kc = a.Kc + (size_t(e) * N + t) * s.szK;
+  float* A = a.A + (size_t(e) * N + t) * n * n;
+  float* B = a.B + (size_t(e) * N + t) * n * m;
+  float* M = a.M + (size_t(e) * N + t) * n * m;
+  float* R = a.R + (size_t(e) * N + t) * m * m;
+  float* K = a.K + (size_t(e) * N + t) * m * n;
+  for (int idx = tid; idx < n * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    A[idx] = (j < nh) ? Ac[i * s.LH + j] : 0.f;
+  }
+  for (int idx = tid; idx < n * m; idx += NT) {
+    const int i = idx / m, j = idx - i * m;
+    B[idx] = Bc[i * s.LMB + j];
+    M[idx] = 0.f;
+  }
+  for (int idx = tid; idx < m * m; idx += NT) {
+    const int i = idx / m, j = idx - i * m;
+    R[idx] = (i == j) ? pk[s.oRd + i] : 0.f;
+  }
+  for (int idx = tid; idx < m * n; idx += NT) {
+    const int i = idx / n, j = idx - i * n;
+    K[idx] = (j < nh) ? Kc[i * s.LH + j] : 0.f;
+  }
+  for (int i = tid; i < m; i += NT) {
+    a.r[(size_t(e) * N + t) * m + i] = pk[s.oR + i];
+    a.k[(size_t(e) * N + t) * m + i] = ok[s.LH + i];
   }
 }
 

@@ -13,4 +13,6 @@ int wb_h1_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const T
   return wb_class_trial<21, 25, 4>(h, dev, io, to, st);
 }
 
+int wb_h1_configure() { return wb_class_configure<21, 25, 4, 6, 320, 96>(false); }
+
 }  // namespace mpxb

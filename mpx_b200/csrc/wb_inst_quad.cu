@@ -17,4 +17,6 @@ int wb_quad_interface(const WbModel& h, const WbModel* dev, const WbiArgs& a, cu
   return wb_class_interface<14, 18, 4>(h, dev, a, st);
 }
 
+int wb_quad_configure() { return wb_class_configure<14, 18, 4, 4, 192, 64>(true); }
+
 }  // namespace mpxb

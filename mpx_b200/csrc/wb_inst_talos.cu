@@ -13,4 +13,6 @@ int wb_talos_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, cons
   return wb_class_trial<32, 28, 8>(h, dev, io, to, st);
 }
 
+int wb_talos_configure() { return wb_class_configure<32, 28, 8, 10, 640, 128>(false); }
+
 }  // namespace mpxb

@@ -193,10 +193,15 @@ __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO&
 #pragma unroll
       for (int k = 1; k < 9; ++k) blk += (a >= bb[k]) ? 1 : 0;
       const int lo = bb[blk], hi = bb[blk + 1];
-      for (int b = lo; b < hi; ++b) {
-        const float rb = cs.r[b];
-        s1 = fmaf(W[a * nw + b], rb, s1);
-        s2 = fmaf(W[b * nw + a], rb, s2);
+      if (o.compact) {  // structured mode: W is diagonal
+        s1 = W[a * nw + a] * cs.r[a];
+        s2 = s1;
+      } else {
+        for (int b = lo; b < hi; ++b) {
+          const float rb = cs.r[b];
+          s1 = fmaf(W[a * nw + b], rb, s1);
+          s2 = fmaf(W[b * nw + a], rb, s2);
+        }
       }
     }
     cs.y[a] = 0.5f * (s1 + s2);
@@ -218,15 +223,76 @@ __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO&
     else gj = cs.rc[j] * cs.y[cs.ra[j]];
     gj = fmaf(0.5f, cs.dpen[j], gj);
     sgrad[j] = gj;
-    o.q[(size_t(e) * (N + 1) + t) * n + j] = gj + satv[j] - Vt[j];
+    float* qdst = o.compact ? o.PK + (size_t(e) * (N + 1) + t) * o.pks + o.oq : o.q + (size_t(e) * (N + 1) + t) * n;
+    qdst[j] = gj + satv[j] - Vt[j];
   }
   if (!term)
     for (int i = tid; i < m; i += NT) {
       const float gi = fmaf(0.5f, cs.dpen[n + i], cs.y[ua0 + i]);
       sgrad[n + i] = gi;
-      o.r[(size_t(e) * N + t) * m + i] = gi + satv[n + i];
+      float* rdst = o.compact ? o.PK + (size_t(e) * (N + 1) + t) * o.pks + o.oR : o.r + (size_t(e) * N + t) * m;
+      rdst[i] = gi + satv[n + i];
     }
 
+}
+
+// Gauss-Newton blocks for a DIAGONAL weight matrix W (every shipped config; the host checks it before selecting the
+// structured path): Q_t = diag + 4x4 quaternion block (+ 3x3 friction-cone blocks on the GRF tail of the quadrupeds),
+// R_t = diag, M_t = 0 -- written into the packed knot block instead of three dense matrices.  Same arithmetic as
+// wb_gn_blocks on the entries that can be non-zero.
+template <int NV, int NC>
+__device__ __forceinline__ void wb_gn_compact(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
+                                              const float* sx, const float* su, const float* sG,
+                                              const WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT) {
+  constexpr int NJ = NV - 6, NF = 3 * NC;
+  const int N = io.N, n = md.n, m = md.m, nj = NJ, nf = NF;
+  const float* W = io.W + size_t(e) * io.w_stride;
+  const int nw = md.nw;
+  const float* contact = ref + 13 + nj + nf;
+  const int ua0 = 12 + 2 * nj + nf;
+  const int g0 = 13 + 2 * nj + nf, v0 = 13 + nj;
+  const bool quad = (md.kind == MPXB_KIND_QUAD_WB);
+  float* pk = o.PK + (size_t(e) * (N + 1) + t) * o.pks;
+  for (int j = tid; j < n; j += NT) {
+    const int aj = cs.ra[j];
+    float v = 0.f;
+    if (aj >= 0) {
+      const float cj = cs.rc[j];
+      v = cj * cj * W[aj * nw + aj];
+      if (quad && j >= v0 && j < v0 + nj) {
+        const float dq = sx[j];
+        v += fminf(fmaxf(penalty_dd(10.01f - dq, 0.1f, 5.f), -1e6f), 1e6f) +
+             fminf(fmaxf(penalty_dd(dq + 10.01f, 0.1f, 5.f), -1e6f), 1e6f);
+      }
+    }
+    pk[o.oQd + j] = v;
+  }
+  for (int idx = tid; idx < 16; idx += NT) {
+    const int i = idx >> 2, k = idx & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) s = fmaf(sG[r * 4 + i], sG[r * 4 + k] * W[(3 + r) * nw + 3 + r], s);
+    pk[o.oQq + idx] = s;
+  }
+  if (quad)
+    for (int idx = tid; idx < 9 * NC; idx += NT) {
+      const int c = idx / 9, a = (idx - 9 * c) / 3, b = idx - 9 * c - 3 * a;
+      const float gx = sx[g0 + 3 * c], gy = sx[g0 + 3 * c + 1], gz = sx[g0 + 3 * c + 2];
+      const float sq = sqrtf(gy * gy + gx * gx + 1e-1f);
+      const float hcone = fminf(fmaxf(penalty_dd(0.5f * gz - sq, 0.1f, 5.f), -1e6f), 1e6f) * contact[c];
+      const float jf3[3] = {-gx / sq, -gy / sq, 0.5f};
+      pk[o.oQc + idx] = hcone * jf3[a] * jf3[b];
+    }
+  if (t < N)
+    for (int i = tid; i < m; i += NT) {
+      float s = W[(ua0 + i) * nw + ua0 + i];
+      if (quad && i < nj) {
+        const float tq = su[i];
+        s += fminf(fmaxf(penalty_dd(44.01f - tq, 1.f, 1.f), -1e6f), 1e6f) +
+             fminf(fmaxf(penalty_dd(tq + 44.01f, 1.f, 1.f), -1e6f), 1e6f);
+      }
+      pk[o.oRd + i] = s;
+    }
 }
 
 template <int NV, int NC>
@@ -534,15 +600,20 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     else wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
     {
       float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
+      float* cpk = o.compact ? o.PK + (size_t(e) * (N + 1) + t + 1) * o.pks + o.oc : nullptr;
       const float* Xn = Xt + n;
-      for (int i = tid; i < n; i += NT) c[i] = sm.k.xn[i] - Xn[i];
+      for (int i = tid; i < n; i += NT) {
+        const float v = sm.k.xn[i] - Xn[i];
+        c[i] = v;
+        if (cpk) cpk[i] = v;
+      }
     }
     wb_tree_acc(md, sm.tr, sm.k.w, sm.k.a, sm.k.z, tid, NT, sync);
     __syncthreads();
     wb_tree_items(md, sm.tr, tid, NT, sync);
     __syncthreads();
-    float* A = o.A + (size_t(e) * N + t) * n * n;
-    float* B = o.B + (size_t(e) * N + t) * n * m;
+    float* A = o.A + (size_t(e) * N + t) * n * o.ldA;
+    float* B = o.B + (size_t(e) * N + t) * n * o.ldB;
     // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
     // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
     wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync);
@@ -560,21 +631,36 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
           dfeet{sm.fold + (3 * NV + NF3) * FW + cc, FW};
       float atv = 0.f;
       float* dst = is_u ? B + (tid - NDS) : A + tid;
-      const int ld = is_u ? m : n;
+      const int ld = is_u ? o.ldB : o.ldA;
       auto sink = [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); };
       if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
       else wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
       satv[is_u ? n + tid - NDS : tid] = atv;
     }
-    // the foot / GRF tail of the state does not enter the dynamics
-    const int ntail = n - NDS;
+    // the foot / GRF tail of the state does not enter the dynamics (structured mode: only the pad columns exist)
+    const int ntail = o.ldA - NDS;
     for (int idx = tid; idx < n * ntail; idx += NT) {
       const int i = idx / ntail, j = NDS + idx - i * ntail;
-      A[i * n + j] = 0.f;
+      A[i * o.ldA + j] = 0.f;
+    }
+    const int nbpad = o.ldB - m;
+    for (int idx = tid; idx < n * nbpad; idx += NT) {
+      const int i = idx / nbpad, j = m + idx - i * nbpad;
+      B[i * o.ldB + j] = 0.f;
     }
   }
   if (t == 0)
-    for (int i = tid; i < n; i += NT) o.c[size_t(e) * (N + 1) * n + i] = io.x0[size_t(e) * n + i] - sx[i];
+    for (int i = tid; i < n; i += NT) {
+      const float v = io.x0[size_t(e) * n + i] - sx[i];
+      o.c[size_t(e) * (N + 1) * n + i] = v;
+      if (o.compact) o.PK[size_t(e) * (N + 1) * o.pks + o.oc + i] = v;
+    }
+  if (o.compact) {
+    // diagonal W: no staging, the Gauss-Newton blocks are a few hundred numbers
+    wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
+    wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, nullptr);
+    return;
+  }
   // stage W over the dead tree / fold arrays (16-byte cp.async when it is 16-byte aligned and fits)
   const float* Wg = io.W + size_t(e) * io.w_stride;
   const float* Wuse = nullptr;
@@ -759,13 +845,6 @@ inline int wb_class_interface(const WbModel& h, const WbModel* dev, const WbiArg
   using S = WbiSmem<NB, NV, NC>;
   if (!h.tree_ok || h.nbody > NB || h.nv != NV || h.nc != NC || h.nj != 3 * NC) return MPXB_EUNSUPPORTED;
   auto kern = wb_interface_kernel<NB, NV, NC, NT>;
-  static bool configured[64] = {};
-  int d = 0;
-  cudaGetDevice(&d);
-  if (d < 64 && !configured[d]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
-    configured[d] = true;
-  }
   kern<<<a.E, NT, sizeof(S), st>>>(dev, a);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
@@ -775,13 +854,6 @@ inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const Mod
   using S = WbLinSmem<NV, NC, MAXD, NT>;
   if (h.nv != NV || h.nc != NC || h.maxdepth > MAXD || 2 * NV + 1 + h.m > NT) return MPXB_EUNSUPPORTED;
   auto kern = wb_linearize_kernel<NV, NC, MAXD, NT>;
-  static bool configured[64] = {};
-  int d = 0;
-  cudaGetDevice(&d);
-  if (d < 64 && !configured[d]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
-    configured[d] = true;
-  }
   kern<<<io.E * (io.N + 1), NT, sizeof(S), st>>>(dev, io, lo);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
@@ -790,13 +862,6 @@ template <int NB, int NV, int NC, int NI, int NT>
 inline int wb_launch_linearize3_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
   using S = WbLin3Smem<NB, NV, NC, NI, NT>;
   auto kern = wb_linearize3_kernel<NB, NV, NC, NI, NT>;
-  static bool configured[64] = {};
-  int d = 0;
-  cudaGetDevice(&d);
-  if (d < 64 && !configured[d]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
-    configured[d] = true;
-  }
   kern<<<io.E * (io.N + 1), NT, sizeof(S), st>>>(dev, io, lo);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
@@ -807,6 +872,7 @@ template <int NB, int NV, int NC, int MAXD, int NI, int NT>
 inline int wb_class_linearize(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st,
                               int force_v2) {
   if (h.tree_ok && !force_v2 && h.nbody <= NB && h.nitems <= NI) return wb_launch_linearize3_t<NB, NV, NC, NI, NT>(h, dev, io, lo, st);
+  if (lo.compact) return MPXB_EUNSUPPORTED;  // the structured layout is written by the v3 kernel only
   return wb_launch_linearize_t<NV, NC, MAXD, NT>(h, dev, io, lo, st);
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -915,6 +981,20 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
   }
 }
 
+// Per-device function attributes (> 48 KB dynamic shared memory) of every kernel of a robot class: called from
+// mpxb_model_create, so that no launch sequence -- possibly under stream capture -- has to touch them.
+template <int NB, int NV, int NC, int MAXD, int NI, int NT>
+inline int wb_class_configure(bool with_interface) {
+  auto set = [](auto kern, size_t bytes) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) == cudaSuccess; };
+  bool ok = set(wb_linearize_kernel<NV, NC, MAXD, NT>, sizeof(WbLinSmem<NV, NC, MAXD, NT>));
+  ok = ok && set(wb_linearize3_kernel<NB, NV, NC, NI, NT>, sizeof(WbLin3Smem<NB, NV, NC, NI, NT>));
+  ok = ok && set(wb_trial3_kernel<NB, NV, NC, 64>, sizeof(WbTrialSmem<NB, NV, NC>));
+  if (with_interface) {
+    if constexpr (NV == 6 + 3 * NC) ok = ok && set(wb_interface_kernel<NB, NV, NC, 64>, sizeof(WbiSmem<NB, NV, NC>));
+  }
+  return ok ? MPXB_OK : MPXB_ECUDA;
+}
+
 template <int NB, int NV, int NC>
 inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to_in, cudaStream_t st) {
   static const int legacy = [] { const char* v = getenv("MPXB_WB_TRIAL"); return (v && v[0] == '1') ? 1 : 0; }();
@@ -940,13 +1020,6 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
     constexpr int NT = 64;
     using S = WbTrialSmem<NB, NV, NC>;
     auto kern = wb_trial3_kernel<NB, NV, NC, NT>;
-    static bool configured[64] = {};
-    int d = 0;
-    cudaGetDevice(&d);
-    if (d < 64 && !configured[d]) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(S))) != cudaSuccess) return MPXB_ECUDA;
-      configured[d] = true;
-    }
     const int items = io.E * to.nia * (io.N + 1);
     kern<<<(second && items > 148 * 32) ? 148 * 32 : items, NT, sizeof(S), st>>>(dev, io, to);
     const int wpb = 4;

@@ -77,11 +77,13 @@ class MpcSolver:
     """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
 
     def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None,
-                 eager_line_search=False, line_search="filter", lq_mode=None):
+                 eager_line_search=False, line_search="filter", lq_mode=None, cost_structure="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_env = int(n_env)
         self.lq_mode = (_lib.LQ_SEQUENTIAL if limited_memory else _lib.LQ_SCAN) if lq_mode is None else int(lq_mode)
         if self.lq_mode == _lib.LQ_SCAN:
@@ -112,6 +114,16 @@ class MpcSolver:
         _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_LINE_SEARCH,
                                                   _lib.LS_MERIT if line_search == "merit" else _lib.LS_FILTER),
                    "mpxb_model_set_option")
+        # cost_structure: "dense" reads the whole weight matrix W; "diagonal" promises a diagonal W and runs the
+        # structured kernels (MPXB_OPT_COST_STRUCTURE, csrc/lq3.cuh; whole-body models with limited_memory=True);
+        # "auto" (default) looks at W the first time a given tensor is passed to solve() and picks for itself
+        if cost_structure not in ("auto", "dense", "diagonal"):
+            raise ValueError(f"cost_structure must be 'auto', 'dense' or 'diagonal', got {cost_structure!r}")
+        self.cost_structure = cost_structure
+        self._w_seen = None
+        self._structured = False
+        self._set_structure(cost_structure == "diagonal")
+        self._expanded = True
         self.ws_bytes = self.lib.mpxb_workspace_bytes(self.handle, self.n_env, self.lq_mode)
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         E = self.n_env
@@ -134,6 +146,22 @@ class MpcSolver:
         lq = 3 + int(self.N).bit_length() if parallel_scan else 1
         self.launches_per_call = (2 + lq + trial) * self.max_iter
 
+    def _set_structure(self, diagonal):
+        self._structured = bool(diagonal)
+        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_COST_STRUCTURE,
+                                                  _lib.COST_DIAGONAL_W if diagonal else _lib.COST_DENSE),
+                   "mpxb_model_set_option")
+
+    def _inspect_W(self, W):
+        """cost_structure="auto": one look (a device reduction + one scalar read) per distinct W tensor."""
+        key = (W.data_ptr(), W._version, tuple(W.shape))
+        if key == self._w_seen:
+            return
+        self._w_seen = key
+        Wm = W if W.dim() == 3 else W[None]
+        off = Wm - torch.diag_embed(torch.diagonal(Wm, dim1=-2, dim2=-1))
+        self._set_structure(not bool(torch.any(off != 0).item()))
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
@@ -145,6 +173,8 @@ class MpcSolver:
     def _chk(self, t, shape, name):
         if not (torch.is_tensor(t) and t.is_cuda):
             raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+        if t.device != self.device:
+            raise RuntimeError(f"{name}: tensor on {t.device}, solver on {self.device}")
         if t.dtype != torch.float32 or not t.is_contiguous():
             t = t.to(torch.float32).contiguous()
         if tuple(t.shape) != tuple(shape):
@@ -162,6 +192,8 @@ class MpcSolver:
         else:
             W = self._chk(W, (E, self.nw, self.nw), "W")
             wstride = self.nw * self.nw
+        if self.cost_structure == "auto" and self.desc.kind != _lib.KIND_SRBD and self.lq_mode == _lib.LQ_SEQUENTIAL:
+            self._inspect_W(W)
         x0 = self._chk(x0, (E, n), "x0")
         X_in = self._chk(X_in, (E, N + 1, n), "X_in")
         U_in = self._chk(U_in, (E, N, m), "U_in")
@@ -172,6 +204,7 @@ class MpcSolver:
             V = torch.empty_like(V_in)
         else:
             X, U, V = out
+        self._expanded = False
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.lib.mpxb_mpc_step(
             self.handle, stream, E, self.lq_mode, self.max_iter,
@@ -185,6 +218,12 @@ class MpcSolver:
 
     def view(self, name):
         """Intermediate of the last call (A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, ls_theta, ls_phi, g, cost, slope)."""
+        if not self._expanded:
+            # the structured path keeps the LQ data packed; write the dense arrays out for inspection
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.mpxb_workspace_expand(self.handle, stream, self.n_env, self.lq_mode,
+                                                      self.workspace.data_ptr()), "mpxb_workspace_expand")
+            self._expanded = True
         cnt = C.c_size_t()
         ptr = self.lib.mpxb_workspace_view(self.handle, self.n_env, self.lq_mode, self.workspace.data_ptr(),
                                            name.encode(), C.byref(cnt))

@@ -14,19 +14,21 @@ from golden_check import load, solve, LIN, LQ, REL_TOL, TOL_CAP  # noqa: E402
 from mpx_b200 import _lib  # noqa: E402
 
 robots = sys.argv[1].split(",") if len(sys.argv) > 1 else ["srbd", "go2", "aliengo", "h1", "talos"]
-modes = {"seq": (_lib.LQ_SEQUENTIAL, ""), "pscan": (_lib.LQ_SCAN_PARALLEL, "_scan"), "sscan": (_lib.LQ_SCAN_SERIAL, "_scan")}
+modes = {"seq": (_lib.LQ_SEQUENTIAL, ""), "seq3": (_lib.LQ_SEQUENTIAL, ""), "pscan": (_lib.LQ_SCAN_PARALLEL, "_scan"), "sscan": (_lib.LQ_SCAN_SERIAL, "_scan")}
 for robot in robots:
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
     segs = parity.segments(cfg)
     for case in ("warm", "second", "cold", "far"):
         g = load(robot, case)
         for mname, (mode, sfx) in modes.items():
-            solver, X, U, V = solve(cfg, g, mode, True)
+            if mname == "seq3" and robot == "srbd":
+                continue
+            solver, X, U, V = solve(cfg, g, mode, True, "diagonal" if mname == "seq3" else "dense")
             E = g["x0"].shape[0]
             worst = {}
             for e in range(E):
                 tol = lambda key: max(REL_TOL, min(4 * g.budget(key, e), TOL_CAP if key.endswith("_scan") else 1.0))
-                items = [(nm, solver.view(nm)[e], g[nm][e], nm) for nm in (LIN if mname == "seq" else ())]
+                items = [(nm, solver.view(nm)[e], g[nm][e], nm) for nm in (LIN if mname in ("seq", "seq3") else ())]
                 items += [(nm, solver.view(nm)[e], g[nm + sfx][e], nm + sfx) for nm in LQ]
                 items += [(nm, got[e], g[nm + sfx][e], nm + sfx) for nm, got in (("X", X), ("U", U), ("V", V))]
                 for nm, got, ref, key in items:

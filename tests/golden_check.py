@@ -43,11 +43,11 @@ def load(robot, case):
     return Fixture(robot, case)
 
 
-def solve(cfg, g, lq_mode, eager=True):
+def solve(cfg, g, lq_mode, eager=True, cost_structure="dense"):
     from mpx_b200.primal_dual_ilqr.optimizers import MpcSolver
     E = g["x0"].shape[0]
     T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).contiguous().cuda()
-    solver = MpcSolver(cfg, E, lq_mode=lq_mode, eager_line_search=eager)
+    solver = MpcSolver(cfg, E, lq_mode=lq_mode, eager_line_search=eager, cost_structure=cost_structure)
     X, U, V = solver.solve(T(g["reference"]), T(g["parameter"]), T(cfg.W), T(g["x0"]), T(g["X0"]), T(g["U0"]), T(g["V0"]))
     torch.cuda.synchronize()
     return solver, X, U, V

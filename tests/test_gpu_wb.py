@@ -26,17 +26,21 @@ ROBOTS = ("go2", "aliengo", "h1", "talos")
 CASES = [(r, c) for r in ROBOTS for c in ("warm", "second", "cold", "far")]
 
 
+@pytest.mark.parametrize("structure", ["dense", "diagonal"])
 @pytest.mark.parametrize("eager", [True, False])
 @pytest.mark.parametrize("robot,case", CASES)
-def test_wb_step_matches_golden(robot, case, eager):
+def test_wb_step_matches_golden(robot, case, eager, structure):
     """Linearisation (A,B,Q,R,M,q,r,c,g), sequential-LQ gains / value function / search direction, line-search
     merit data, accepted step and the new iterate of one optimizers.mpc call.  eager: all 11 trial points are
     evaluated like the reference's vmap; lazy (the default): alpha = 1 first, the rest only where it is rejected --
-    the accepted step and the new iterate must not change."""
+    the accepted step and the new iterate must not change.  structure: "dense" reads the whole weight matrix W and
+    runs the general kernels; "diagonal" (what the wrappers select for the shipped configs, whose W is diagonal) runs
+    the structured linearise / LQ kernels (csrc/lq3.cuh) -- both must reproduce the same fixture."""
     from mpx_b200 import _lib
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
     g = _load(robot, case)
-    solver, X, U, V = _solve(cfg, g, _lib.LQ_SEQUENTIAL, eager)
+    solver, X, U, V = _solve(cfg, g, _lib.LQ_SEQUENTIAL, eager, structure)
+    assert solver._structured == (structure == "diagonal")
     _check_step(cfg, g, solver, X, U, V, "", eager)
 
 
