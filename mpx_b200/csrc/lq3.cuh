@@ -22,9 +22,14 @@
 // UBLKCP in SASS) that completes on an mbarrier (transaction count); results leave shared memory the same way
 // (cp.async.bulk.global.shared::cta + bulk groups).  No thread computes a global address inside the knot loop.
 //
-// Compute: 64 threads per CTA (one CTA per environment), 8x8 / 8x4 / 4x8 register tiles on k-major shared-memory
-// operands read as float4: 4 FMA per shared-memory float loaded, which is the balance point of the SM
-// (128 FMA lanes against 32 shared-memory words per clock) -- the 4x4 tiles of lq.cuh are shared-memory bound by 2x.
+// Compute: 128 threads per CTA (one CTA per environment).  A_t and B_t sit side by side in one k-major block
+// AB = [A_t | B_t] ([n][LAB]), so the two products of a Riccati step are ONE product each with a uniform tile shape:
+//   TP  = P+ AB            = [T1 | PB]                       (head rows; K extent nh)
+//   XHG = AB' TP           = [[X, .], [H, G]]                (only the upper tiles of the symmetric X; K extent n)
+// 4x8 register tiles on float4 operand loads (2.7 FMA per shared-memory float; the 4x4 tiles of lq.cuh are at 2), every
+// lane of a warp runs the same instruction stream, tiles are packed densely into the leading warps and the remaining
+// warps take the vector work (w, h, q') of the same stage; the warp roles rotate with the CTA index so that the heavy
+// warps of co-resident CTAs land on different SM sub-partitions.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,8 +41,10 @@ namespace mpxb {
 // Dimensions and packed layouts shared by the linearise kernels (writers), this kernel and the expand kernel.
 template <int NH_, int NTL_, int M_, int NCONE_> struct Lq3Dims {
   static constexpr int NH = NH_, NTL = NTL_, M = M_, NCONE = NCONE_, n = NH_ + NTL_;
-  static constexpr int LH = (NH_ + 7) & ~7;    // padded head: row stride of A, P_hh, K, H
-  static constexpr int LMB = (M_ + 3) & ~3;    // padded control dim: row stride of B, PB, G
+  static constexpr int LH = (NH_ + 7) & ~7;    // padded head: row stride of P_hh and K, columns of A inside AB
+  static constexpr int LM8 = (M_ + 7) & ~7;    // columns of B inside AB
+  static constexpr int LAB = LH + LM8;         // row stride of AB = [A_t | B_t], TP, XHG
+  static constexpr int LMB = (M_ + 3) & ~3;    // padded control dim of the packed vectors and of K's rows
   static constexpr int LN = (n + 3) & ~3;
   // packed knot block PK[t] (floats): diag(Q_t) | q_t | c_t | quaternion block of Q_t (4x4) | cone blocks (NCONE x 3x3)
   // | diag(R_t) | r_t
@@ -45,28 +52,27 @@ template <int NH_, int NTL_, int M_, int NCONE_> struct Lq3Dims {
   static constexpr int oRd = oQc + ((9 * NCONE_ + 3) & ~3), oR = oRd + LMB, PKS = oR + LMB;
   static constexpr int OKS = LH + LMB;         // packed result block OK[t]: p_t head | k_t
   static constexpr int cone0 = n - 3 * NCONE_;  // first state index of the cone blocks (the GRF tail of a quadruped)
-  static constexpr int szA = n * LH, szB = n * LMB, szP = LH * LH, szK = LMB * LH;  // floats per knot
+  static constexpr int szAB = n * LAB, szP = LH * LH, szK = LMB * LH;  // floats per knot
 };
 
 // Runtime mirror of Lq3Dims (host side: workspace layout, views)
 struct Lq3Layout {
-  int nh, ntl, m, ncone, n, LH, LMB, LN, oQd, oq, oc, oQq, oQc, oRd, oR, PKS, OKS, cone0, szA, szB, szP, szK;
+  int nh, ntl, m, ncone, n, LH, LM8, LAB, LMB, LN, oQd, oq, oc, oQq, oQc, oRd, oR, PKS, OKS, cone0, szAB, szP, szK;
 };
 inline Lq3Layout lq3_layout(int nh, int ntl, int m, int ncone) {
   Lq3Layout L;
   L.nh = nh; L.ntl = ntl; L.m = m; L.ncone = ncone; L.n = nh + ntl;
-  L.LH = (nh + 7) & ~7; L.LMB = (m + 3) & ~3; L.LN = (L.n + 3) & ~3;
+  L.LH = (nh + 7) & ~7; L.LM8 = (m + 7) & ~7; L.LAB = L.LH + L.LM8; L.LMB = (m + 3) & ~3; L.LN = (L.n + 3) & ~3;
   L.oQd = 0; L.oq = L.LN; L.oc = 2 * L.LN; L.oQq = 3 * L.LN; L.oQc = L.oQq + 16;
   L.oRd = L.oQc + ((9 * ncone + 3) & ~3); L.oR = L.oRd + L.LMB; L.PKS = L.oR + L.LMB;
   L.OKS = L.LH + L.LMB; L.cone0 = L.n - 3 * ncone;
-  L.szA = L.n * L.LH; L.szB = L.n * L.LMB; L.szP = L.LH * L.LH; L.szK = L.LMB * L.LH;
+  L.szAB = L.n * L.LAB; L.szP = L.LH * L.LH; L.szK = L.LMB * L.LH;
   return L;
 }
 
 struct Lq3Args {
   int E, N;
-  const float *A;    // [E][N][n][LH]     leading nh columns live, the rest zero
-  const float *B;    // [E][N][n][LMB]
+  const float *AB;   // [E][N][n][LAB]    [A_t | B_t]: columns nh..LH-1 and LH+m..LAB-1 are zero
   const float *PK;   // [E][N+1][PKS]
   float *Kc;         // [E][N][LMB][LH]   rows >= m and columns >= nh are zero
   float *Pc;         // [E][N+1][LH][LH]  head block of P_t
@@ -109,97 +115,62 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ register tiles
-// acc[TI][TJ] += A[0:K, i0:i0+TI]^T B[0:K, j0:j0+TJ]   (both operands k-major in shared memory, float4 loads)
-template <int TI, int TJ>
-__device__ __forceinline__ void rt_atb(float (&acc)[TI][TJ], const float* __restrict__ A, int lda, int i0,
-                                       const float* __restrict__ B, int ldb, int j0, int K) {
-  const float* pa = A + i0;
-  const float* pb = B + j0;
-#pragma unroll 2
+// acc[4][8] += L[0:K, i0:i0+4]^T R[0:K, j0:j0+8]   (both operands k-major in shared memory, float4 loads)
+__device__ __forceinline__ void rt48_atb(float (&acc)[4][8], const float* __restrict__ L, int ldl, const float* __restrict__ R,
+                                         int ldr, int K) {
+#pragma unroll 4
   for (int kk = 0; kk < K; ++kk) {
-    float av[TI], bv[TJ];
+    const float4 l4 = *reinterpret_cast<const float4*>(L);
+    const float4 r0 = *reinterpret_cast<const float4*>(R);
+    const float4 r1 = *reinterpret_cast<const float4*>(R + 4);
+    const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+    const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-    for (int x = 0; x < TI; x += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(pa + x);
-      av[x] = t.x; av[x + 1] = t.y; av[x + 2] = t.z; av[x + 3] = t.w;
-    }
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
-    for (int y = 0; y < TJ; y += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(pb + y);
-      bv[y] = t.x; bv[y + 1] = t.y; bv[y + 2] = t.z; bv[y + 3] = t.w;
-    }
-#pragma unroll
-    for (int x = 0; x < TI; ++x)
-#pragma unroll
-      for (int y = 0; y < TJ; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
-    pa += lda;
-    pb += ldb;
+      for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(lv[x], rv[y], acc[x][y]);
+    L += ldl;
+    R += ldr;
   }
 }
-template <int TI, int TJ> __device__ __forceinline__ void rt_zero(float (&acc)[TI][TJ]) {
-#pragma unroll
-  for (int x = 0; x < TI; ++x)
-#pragma unroll
-    for (int y = 0; y < TJ; ++y) acc[x][y] = 0.f;
-}
-template <int TI, int TJ>
-__device__ __forceinline__ void rt_store(float* __restrict__ C, int ldc, int i0, int j0, const float (&acc)[TI][TJ]) {
-#pragma unroll
-  for (int x = 0; x < TI; ++x)
-#pragma unroll
-    for (int y = 0; y < TJ; y += 4)
-      *reinterpret_cast<float4*>(C + (i0 + x) * ldc + j0 + y) = make_float4(acc[x][y], acc[x][y + 1], acc[x][y + 2], acc[x][y + 3]);
-}
-// rows >= row_end are not stored (the head tiles of T1 / PB overlap the first tail rows, which are written elsewhere)
-template <int TI, int TJ>
-__device__ __forceinline__ void rt_store_rows(float* __restrict__ C, int ldc, int i0, int j0, const float (&acc)[TI][TJ], int row_end) {
-#pragma unroll
-  for (int x = 0; x < TI; ++x)
-    if (i0 + x < row_end) {
-#pragma unroll
-      for (int y = 0; y < TJ; y += 4)
-        *reinterpret_cast<float4*>(C + (i0 + x) * ldc + j0 + y) = make_float4(acc[x][y], acc[x][y + 1], acc[x][y + 2], acc[x][y + 3]);
-    }
-}
-template <int TI, int TJ>
-__device__ __forceinline__ void rt_load(float (&acc)[TI][TJ], const float* __restrict__ C, int ldc, int i0, int j0) {
-#pragma unroll
-  for (int x = 0; x < TI; ++x)
-#pragma unroll
-    for (int y = 0; y < TJ; y += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(C + (i0 + x) * ldc + j0 + y);
-      acc[x][y] = t.x; acc[x][y + 1] = t.y; acc[x][y + 2] = t.z; acc[x][y + 3] = t.w;
-    }
-}
 
-// Shared-memory arena (floats).  The rollout reuses it as two stages of {K, A, B, P, PK, OK}.
+// Shared-memory arena (floats).  The rollout reuses it as two stages of {K, AB, P, PK, OK}.
 template <class D> struct Lq3Smem {
-  static constexpr int LH = D::LH, LMB = D::LMB, LN = D::LN, n = D::n;
-  static constexpr int TROWS = (n + 3) & ~3;            // rows of T1 / PB (k extent of the second products)
-  static constexpr int oP0 = 0;                         // P ping  [LH][LH]
-  static constexpr int oP1 = oP0 + LH * LH;             // P pong
-  static constexpr int oA = oP1 + LH * LH;              // A_t  [n][LH]
-  static constexpr int oT = oA + D::szA;                // T1   [TROWS][LH]
-  static constexpr int oB = oT + TROWS * LH;            // B_t  [n][LMB]
-  static constexpr int oPB = oB + D::szB;               // PB   [TROWS][LMB]
-  static constexpr int oH = oPB + TROWS * LMB;          // H    [LMB][LH]
-  static constexpr int oG = oH + LMB * LH;              // G    [LMB][LMB]
-  static constexpr int oK = oG + LMB * LMB;             // K    [LMB][LH]
+  static constexpr int LH = D::LH, LAB = D::LAB, LMB = D::LMB, LN = D::LN, n = D::n;
+  static constexpr int RX = LH + LMB;                   // rows of XHG: X rows, then H | G rows
+  static constexpr int NL2 = (LH / 4) * (LH / 8) + (LMB / 4) * (LAB / 8);  // upper bound of the S2 tile list
+  static constexpr int oP = 0;                          // P_hh [LH][LH]
+  static constexpr int oAB = oP + LH * LH;              // [A_t | B_t]  [n][LAB]
+  static constexpr int oTP = oAB + D::szAB;             // [T1 | PB]    [n][LAB]
+  static constexpr int oXG = oTP + n * LAB + ((n * LAB) & 3);   // [[X, .], [H, G]]  [RX][LAB]
+  static constexpr int oK = oXG + RX * LAB;             // K [LMB][LH]
   static constexpr int oPK0 = oK + LMB * LH;            // PK ping / pong
   static constexpr int oPK1 = oPK0 + D::PKS;
   static constexpr int oOK = oPK1 + D::PKS;             // OK staging: p head | k
-  static constexpr int oVec = oOK + D::OKS;             // p [LN] | w [LN] | qh [LH] | h [LMB] | gi [LMB]
-  static constexpr int backward = oVec + 2 * LN + LH + 2 * LMB;
-  static constexpr int stage = D::szK + D::szA + D::szB + D::szP + D::PKS + D::OKS;
+  static constexpr int oVec = oOK + D::OKS;             // p [LN] | w [LN] | hq [LAB] | gi [LMB]
+  static constexpr int oList = oVec + 2 * LN + LAB + LMB;   // S2 tile list (one int per tile)
+  static constexpr int backward = oList + ((NL2 + 3) & ~3);
+  static constexpr int stage = D::szK + D::szAB + D::szP + D::PKS + D::OKS;
   static constexpr int rollout = 2 * stage + 2 * LN + LMB + 8;
   static constexpr int total = (backward > rollout ? backward : rollout) + 8;   // + mbarriers (4 x 8 bytes)
   static constexpr size_t bytes = size_t(total) * sizeof(float);
 };
 
-// resident CTAs per SM the shared-memory footprint allows (capped at 6)
+// resident CTAs per SM the shared-memory footprint allows (capped at 4)
 template <class D> __host__ __device__ constexpr int lq3_min_blocks() {
   constexpr int b = int(232448 / (Lq3Smem<D>::bytes + 1024));
-  return b < 1 ? 1 : (b > 6 ? 6 : b);
+  return b < 1 ? 1 : (b > 4 ? 4 : b);
+}
+
+// contribution of the sparse tail of P+ (= tail of Q_{t+1}: diag + 3x3 cone blocks) to row r >= NH of  P+ v
+template <class D> __device__ __forceinline__ float lq3_tail_row(const float* __restrict__ pk, int r, const float* __restrict__ v, int ldv) {
+  float s = pk[D::oQd + r] * v[r * ldv];
+  if (D::NCONE > 0 && r >= D::cone0) {
+    const int blk = (r - D::cone0) / 3, k0 = D::cone0 + 3 * blk, ri = r - k0;
+    const float* cb = pk + D::oQc + 9 * blk + 3 * ri;
+    s = fmaf(cb[0], v[k0 * ldv], fmaf(cb[1], v[(k0 + 1) * ldv], fmaf(cb[2], v[(k0 + 2) * ldv], s)));
+  }
+  return s;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -207,32 +178,32 @@ template <int NH, int NTL, int M, int NCONE, int NT>
 __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>()) lq3_kernel(Lq3Args a) {
   using D = Lq3Dims<NH, NTL, M, NCONE>;
   using S = Lq3Smem<D>;
-  constexpr int LH = D::LH, LMB = D::LMB, LN = D::LN, n = D::n, m = M, TROWS = S::TROWS;
-  constexpr int TH = LH / 8, TM4 = LMB / 4;
+  constexpr int LH = D::LH, LAB = D::LAB, LMB = D::LMB, LN = D::LN, n = D::n, m = M;
+  constexpr int RB1 = LH / 4, CB = LAB / 8, CBH = LH / 8, RBH = LMB / 4, NW = NT / 32;
+  constexpr int NT1 = RB1 * CB;   // tiles of TP = P+ AB
   extern __shared__ __align__(128) float smem3[];
   float* const smem = smem3;
   const int e = blockIdx.x, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
-  float* sPb[2] = {smem + S::oP0, smem + S::oP1};
-  float* sA = smem + S::oA;
-  float* sT = smem + S::oT;
-  float* sB = smem + S::oB;
-  float* sPB = smem + S::oPB;
-  float* sH = smem + S::oH;
-  float* sG = smem + S::oG;
+  // warp roles rotate with the CTA index (co-resident CTAs b, b + #SM, ... then keep their tile warps on different
+  // sub-partitions); vt is the thread's index in the work lists
+  const int rot = (blockIdx.x + blockIdx.x / 148) % NW;
+  const int vt = (((tid >> 5) + rot) % NW) * 32 + (tid & 31);
+  float* sP = smem + S::oP;
+  float* sAB = smem + S::oAB;
+  float* sTP = smem + S::oTP;
+  float* sXG = smem + S::oXG;
   float* sK = smem + S::oK;
-  float* sPKb[2] = {smem + S::oPK0, smem + S::oPK1};
   float* sOK = smem + S::oOK;
   float* sp = smem + S::oVec;   // p_{t+1} (full n)
-  float* sw = sp + LN;          // w = p + P c
-  float* sqh = sw + LN;         // q_h + Az' w   [LH]
-  float* sh = sqh + LH;         // h [LMB]
-  float* sgi = sh + LMB;        // 1 / diag(chol G) [LMB]
+  float* sw = sp + LN;          // w = p+ + P+ c
+  float* shq = sw + LN;         // [q_h + Az' w | B' w + r]   [LAB]
+  float* sgi = shq + LAB;       // 1 / diag(chol G) [LMB]
+  int* list2 = reinterpret_cast<int*>(smem + S::oList);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::total - 8);   // [0] backward loads, [1..2] rollout stages
 
-  const float* gA = a.A + size_t(e) * N * D::szA;
-  const float* gB = a.B + size_t(e) * N * D::szB;
+  const float* gAB = a.AB + size_t(e) * N * D::szAB;
   const float* gPK = a.PK + size_t(e) * (N + 1) * D::PKS;
   float* gK = a.Kc + size_t(e) * N * D::szK;
   float* gP = a.Pc + size_t(e) * (N + 1) * D::szP;
@@ -245,245 +216,303 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
     mbar_fence_init();
   }
   __syncthreads();
-  // first loads: A_{N-1}, B_{N-1}, PK[N] (terminal) and PK[N-1]
+  // first loads: AB_{N-1}, PK[N] (terminal) and PK[N-1]
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], uint32_t((D::szA + D::szB + 2 * D::PKS) * sizeof(float)));
-    bulk_g2s(sA, gA + size_t(N - 1) * D::szA, D::szA * sizeof(float), &bars[0]);
-    bulk_g2s(sB, gB + size_t(N - 1) * D::szB, D::szB * sizeof(float), &bars[0]);
-    bulk_g2s(sPKb[0], gPK + size_t(N) * D::PKS, D::PKS * sizeof(float), &bars[0]);
-    bulk_g2s(sPKb[1], gPK + size_t(N - 1) * D::PKS, D::PKS * sizeof(float), &bars[0]);
+    mbar_expect_tx(&bars[0], uint32_t((D::szAB + 2 * D::PKS) * sizeof(float)));
+    bulk_g2s(sAB, gAB + size_t(N - 1) * D::szAB, D::szAB * sizeof(float), &bars[0]);
+    bulk_g2s(smem + S::oPK0, gPK + size_t(N) * D::PKS, D::PKS * sizeof(float), &bars[0]);
+    bulk_g2s(smem + S::oPK1, gPK + size_t(N - 1) * D::PKS, D::PKS * sizeof(float), &bars[0]);
   }
-  // zero what no copy ever writes: the pad rows of T1 / PB (k extent TROWS > n), H / K / G pad rows, vectors
-  for (int i = tid; i < (TROWS - n) * LH; i += NT) sT[n * LH + i] = 0.f;
-  for (int i = tid; i < (TROWS - n) * LMB; i += NT) sPB[n * LMB + i] = 0.f;
-  for (int i = tid; i < LMB * LH; i += NT) { sH[i] = 0.f; sK[i] = 0.f; }
-  for (int i = tid; i < LMB * LMB; i += NT) sG[i] = 0.f;
-  for (int i = tid; i < 2 * LN + LH + 2 * LMB; i += NT) sp[i] = 0.f;
+  // S2 tile list: the upper tiles of X (row block ri, column block cj with 4 ri <= 8 cj + 7), then H, then G
+  int nXU = 0, nS2 = 0;
+  for (int cj = 0; cj < CBH; ++cj)
+    for (int ri = 0; ri < RB1 && ri <= 2 * cj + 1; ++ri) {
+      if (tid == 0) list2[nXU] = (ri << 8) | cj;
+      ++nXU;
+    }
+  nS2 = nXU;
+  for (int ri = RB1; ri < RB1 + RBH; ++ri)
+    for (int cj = 0; cj < CB; ++cj) {
+      if (cj >= CBH && 8 * (cj - CBH) >= m) continue;
+      if (tid == 0) list2[nS2] = (ri << 8) | cj;
+      ++nS2;
+    }
+  // zero what no copy ever writes
+  for (int i = tid; i < LH * LH; i += NT) sP[i] = 0.f;
+  for (int i = tid; i < n * LAB; i += NT) sTP[i] = 0.f;
+  for (int i = tid; i < S::RX * LAB; i += NT) sXG[i] = 0.f;
+  for (int i = tid; i < LMB * LH; i += NT) sK[i] = 0.f;
+  for (int i = tid; i < 2 * LN + LAB + LMB; i += NT) sp[i] = 0.f;
   for (int i = tid; i < D::OKS; i += NT) sOK[i] = 0.f;
+  __syncthreads();
   uint32_t ph0 = 0;
   mbar_wait(&bars[0], ph0);
   ph0 ^= 1;
   // terminal value function: P_N = Q_N, p_N = q_N (primal_tvlqr.py:136); head block expanded to dense
-  int cur = 0;
   {
-    const float* pkN = sPKb[0];
-    float* P = sPb[0];
-    for (int i = tid; i < LH * LH; i += NT) {
-      const int r = i / LH, c = i - r * LH;
-      float v = 0.f;
-      if (r == c && r < NH) v = pkN[D::oQd + r];
-      if (r >= 3 && r < 7 && c >= 3 && c < 7) v = pkN[D::oQq + (r - 3) * 4 + (c - 3)];
-      P[i] = v;
-    }
+    const float* pkN = smem + S::oPK0;
+    for (int i = tid; i < NH; i += NT) sP[i * LH + i] = pkN[D::oQd + i];
+    __syncthreads();
+    if (tid < 16) sP[(3 + (tid >> 2)) * LH + 3 + (tid & 3)] = pkN[D::oQq + tid];
     for (int i = tid; i < n; i += NT) sp[i] = pkN[D::oq + i];
     for (int i = tid; i < LH; i += NT) sOK[i] = (i < NH) ? pkN[D::oq + i] : 0.f;
   }
   __syncthreads();
   fence_async_smem();
   if (tid == 0) {
-    bulk_s2g(gP + size_t(N) * D::szP, sPb[0], D::szP * sizeof(float));
+    bulk_s2g(gP + size_t(N) * D::szP, sP, D::szP * sizeof(float));
     bulk_s2g(gOK + size_t(N) * D::OKS, sOK, D::OKS * sizeof(float));
     bulk_commit();
   }
   int pkn = 0;  // buffer that holds PK[t+1]; PK[t] is in the other one
 
   for (int t = N - 1; t >= 0; --t) {
-    const float* P = sPb[cur];        // P_{t+1} head (symmetric)
-    float* X = sPb[cur ^ 1];          // X, XY, then P_t
-    const float* pk1 = sPKb[pkn];      // PK[t+1]: c_{t+1}, tail of Q_{t+1} (= tail of P_{t+1})
-    const float* pk0 = sPKb[pkn ^ 1];  // PK[t]:   Q_t, q_t, R_t, r_t
-    // ---- S1: T1 = P+ Az, PB = P+ B (head rows by tiles, tail rows sparse), w = p+ + P+ c
-    for (int tile = tid; tile < TH * TH + TH * TM4; tile += NT) {
-      if (tile < TH * TH) {
-        const int i0 = (tile / TH) * 8, j0 = (tile % TH) * 8;
-        float acc[8][8];
-        rt_zero(acc);
-        rt_atb<8, 8>(acc, P, LH, i0, sA, LH, j0, NH);
-        rt_store_rows<8, 8>(sT, LH, i0, j0, acc, NH);
+    const float* pk1 = smem + (pkn ? S::oPK1 : S::oPK0);   // PK[t+1]: c_{t+1}, tail of Q_{t+1} (= tail of P_{t+1})
+    const float* pk0 = smem + (pkn ? S::oPK0 : S::oPK1);   // PK[t]:   Q_t, q_t, R_t, r_t
+    // ---- S1: TP = P+ AB (head rows by tiles, tail rows sparse), w = p+ + P+ c
+    for (int it = vt; it < NT1 + NTL * (LAB / 4) + n; it += NT) {
+      if (it < NT1) {
+        const int ri = it / CB, cj = it - ri * CB;
+        float acc[4][8];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+        rt48_atb(acc, sP + 4 * ri, LH, sAB + 8 * cj, LAB, NH);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          if (4 * ri + x < NH) {   // rows NH.. of the last row block are tail rows, written below
+            float* dst = sTP + (4 * ri + x) * LAB + 8 * cj;
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[x][4], acc[x][5], acc[x][6], acc[x][7]);
+          }
+      } else if (it < NT1 + NTL * (LAB / 4)) {
+        const int q = it - NT1;
+        const int r = NH + q / (LAB / 4), c4 = 4 * (q % (LAB / 4));
+        float4 v;
+        v.x = lq3_tail_row<D>(pk1, r, sAB + c4, LAB);
+        v.y = lq3_tail_row<D>(pk1, r, sAB + c4 + 1, LAB);
+        v.z = lq3_tail_row<D>(pk1, r, sAB + c4 + 2, LAB);
+        v.w = lq3_tail_row<D>(pk1, r, sAB + c4 + 3, LAB);
+        *reinterpret_cast<float4*>(sTP + r * LAB + c4) = v;
       } else {
-        const int tt = tile - TH * TH;
-        const int i0 = (tt / TM4) * 8, j0 = (tt % TM4) * 4;
-        float acc[8][4];
-        rt_zero(acc);
-        rt_atb<8, 4>(acc, P, LH, i0, sB, LMB, j0, NH);
-        rt_store_rows<8, 4>(sPB, LMB, i0, j0, acc, NH);
-      }
-    }
-    // tail rows r = NH .. n-1 of T1 / PB: P_tt = diag(Qd) (+ 3x3 cone blocks), rows of A / B below the head
-    for (int idx = tid; idx < NTL * (LH + LMB) + n; idx += NT) {
-      if (idx < NTL * (LH + LMB)) {
-        const int rr = idx / (LH + LMB), cc = idx - rr * (LH + LMB);
-        const int r = NH + rr;
-        const bool isA = cc < LH;
-        const float* src = isA ? sA + cc : sB + (cc - LH);
-        const int ld = isA ? LH : LMB;
-        float v = pk1[D::oQd + r] * src[r * ld];
-        if (NCONE > 0 && r >= D::cone0) {
-          const int blk = (r - D::cone0) / 3, k0 = D::cone0 + 3 * blk, ri = r - k0;
-          const float* cb = pk1 + D::oQc + 9 * blk + 3 * ri;
-          v = fmaf(cb[0], src[k0 * ld], fmaf(cb[1], src[(k0 + 1) * ld], fmaf(cb[2], src[(k0 + 2) * ld], v)));
-        }
-        if (isA) sT[r * LH + cc] = v; else sPB[r * LMB + (cc - LH)] = v;
-      } else {
-        const int i = idx - NTL * (LH + LMB);
+        const int i = it - NT1 - NTL * (LAB / 4);
         const float* cv = pk1 + D::oc;
         float s = sp[i];
         if (i < NH) {
-          for (int j = 0; j < NH; ++j) s = fmaf(P[j * LH + i], cv[j], s);
+          for (int j = 0; j < NH; ++j) s = fmaf(sP[j * LH + i], cv[j], s);
         } else {
-          s = fmaf(pk1[D::oQd + i], cv[i], s);
-          if (NCONE > 0 && i >= D::cone0) {
-            const int blk = (i - D::cone0) / 3, k0 = D::cone0 + 3 * blk, ri = i - k0;
-            const float* cb = pk1 + D::oQc + 9 * blk + 3 * ri;
-            s = fmaf(cb[0], cv[k0], fmaf(cb[1], cv[k0 + 1], fmaf(cb[2], cv[k0 + 2], s)));
-          }
+          s += lq3_tail_row<D>(pk1, i, cv, 1);
         }
         sw[i] = s;
       }
     }
     __syncthreads();
-    // ---- S2: X = Az' T1, H = B' T1, G = B' PB, h = B' w + r, qh = q_h + Az' w
-    for (int tile = tid; tile < TH * TH + TM4 * TH + TM4 * TM4 + LMB + LH; tile += NT) {
-      if (tile < TH * TH) {
-        const int i0 = (tile / TH) * 8, j0 = (tile % TH) * 8;
-        float acc[8][8];
-        rt_zero(acc);
-        rt_atb<8, 8>(acc, sA, LH, i0, sT, LH, j0, n);
-        rt_store<8, 8>(X, LH, i0, j0, acc);
-      } else if (tile < TH * TH + TM4 * TH) {
-        const int tt = tile - TH * TH;
-        const int i0 = (tt / TH) * 4, j0 = (tt % TH) * 8;
+    // ---- S2: XHG = AB' TP on the listed tiles; hq = [q_h | r] + AB' w
+    for (int it = vt; it < nS2 + LH + m; it += NT) {
+      if (it < nS2) {
+        const int code = list2[it];
+        const int ri = code >> 8, cj = code & 255;
         float acc[4][8];
-        rt_zero(acc);
-        rt_atb<4, 8>(acc, sB, LMB, i0, sT, LH, j0, n);
-        rt_store<4, 8>(sH, LH, i0, j0, acc);
-      } else if (tile < TH * TH + TM4 * TH + TM4 * TM4) {
-        const int tt = tile - TH * TH - TM4 * TH;
-        const int i0 = (tt / TM4) * 4, j0 = (tt % TM4) * 4;
-        float acc[4][4];
-        rt_zero(acc);
-        rt_atb<4, 4>(acc, sB, LMB, i0, sPB, LMB, j0, n);
-        rt_store<4, 4>(sG, LMB, i0, j0, acc);
-      } else if (tile < TH * TH + TM4 * TH + TM4 * TM4 + LMB) {
-        const int i = tile - TH * TH - TM4 * TH - TM4 * TM4;
-        float s = (i < m) ? pk0[D::oR + i] : 0.f;
-        for (int j = 0; j < n; ++j) s = fmaf(sB[j * LMB + i], sw[j], s);
-        sh[i] = (i < m) ? s : 0.f;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+        rt48_atb(acc, sAB + 4 * ri, LAB, sTP + 8 * cj, LAB, n);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          float* dst = sXG + (4 * ri + x) * LAB + 8 * cj;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[x][4], acc[x][5], acc[x][6], acc[x][7]);
+        }
       } else {
-        const int i = tile - TH * TH - TM4 * TH - TM4 * TM4 - LMB;
-        float s = (i < NH) ? pk0[D::oq + i] : 0.f;
-        for (int j = 0; j < n; ++j) s = fmaf(sA[j * LH + i], sw[j], s);
-        sqh[i] = (i < NH) ? s : 0.f;
+        const int c = it - nS2;   // column of AB: 0..LH-1 (A part), LH..LH+m-1 (B part)
+        float s = 0.f;
+        if (c < NH) s = pk0[D::oq + c];
+        else if (c >= LH) s = pk0[D::oR + c - LH];
+        for (int j = 0; j < n; ++j) s = fmaf(sAB[j * LAB + c], sw[j], s);
+        shq[c] = (c < NH || c >= LH) ? s : 0.f;
       }
     }
     __syncthreads();
-    // A_t, B_t and PK[t+1] are dead: fetch knot t-1 while S3..S7 run.  The bulk stores of the previous knot have long
-    // finished reading K / OK / P (they were issued a whole S1 + S2 ago); wait for them before those buffers are rewritten.
+    // AB_t and PK[t+1] are dead: fetch knot t-1 while S3..S7 run.  The bulk stores of the previous knot have long
+    // finished reading P / K / OK (issued a whole S1 + S2 ago); wait for them before those buffers are rewritten.
     if (tid == 0) {
       bulk_wait_read0();
       if (t > 0) {
-        mbar_expect_tx(&bars[0], uint32_t((D::szA + D::szB + D::PKS) * sizeof(float)));
-        bulk_g2s(sA, gA + size_t(t - 1) * D::szA, D::szA * sizeof(float), &bars[0]);
-        bulk_g2s(sB, gB + size_t(t - 1) * D::szB, D::szB * sizeof(float), &bars[0]);
-        bulk_g2s(sPKb[pkn], gPK + size_t(t - 1) * D::PKS, D::PKS * sizeof(float), &bars[0]);
+        mbar_expect_tx(&bars[0], uint32_t((D::szAB + D::PKS) * sizeof(float)));
+        bulk_g2s(sAB, gAB + size_t(t - 1) * D::szAB, D::szAB * sizeof(float), &bars[0]);
+        bulk_g2s(smem + (pkn ? S::oPK1 : S::oPK0), gPK + size_t(t - 1) * D::PKS, D::PKS * sizeof(float), &bars[0]);
       }
     }
-    // ---- S3: G = sym(R + G), R = diag (M = 0: H needs no correction)
-    for (int idx = tid; idx < m * m; idx += NT) {
-      const int i = idx / m, j = idx - i * m;
-      if (i <= j) {
-        float gij = sG[i * LMB + j], gji = sG[j * LMB + i];
-        if (i == j) { const float rd = pk0[D::oRd + i]; gij += rd; gji += rd; }
-        const float s = 0.5f * (gij + gji);
-        sG[i * LMB + j] = s;
-        sG[j * LMB + i] = s;
-      }
-    }
-    __syncthreads();
-    // ---- S4: Cholesky G = L L' in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
-    if (tid < 32) {
-      for (int j = 0; j < m; ++j) {
-        float d = sG[j * LMB + j];
-        for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LMB + k2], sG[j * LMB + k2], d);
-        const float inv = 1.f / sqrtf(d);
-        __syncwarp();
-        if (tid == 0) sgi[j] = inv;
-        for (int i = j + 1 + tid; i < m; i += 32) {
-          float s = sG[i * LMB + j];
-          for (int k2 = 0; k2 < j; ++k2) s = fmaf(-sG[i * LMB + k2], sG[j * LMB + k2], s);
-          sG[i * LMB + j] = s * inv;
+    float* sH = sXG + LH * LAB;        // H [m][.] : columns 0..LH-1;  G: columns LH..LH+m-1
+    float* sG = sH + LH;               // G[i][j] = sG[i * LAB + j]
+    if constexpr (M <= 16) {
+      // ---- S3 + S4 + S5 in registers: every right-hand-side column thread forms G = sym(R + B'PB) (R = diag; M = 0:
+      // H needs no correction), factors it (Cholesky, lower; a non-SPD G gives NaN like jax cho_factor) and solves its
+      // own column of [K k] = -G^-1 [H h].  The factorisation is repeated by every column thread -- (m^3)/3 FMAs that
+      // replace a one-warp serial phase and two block barriers per knot.
+      for (int col = tid; col <= NH; col += NT) {
+        // lower triangle, packed row-wise: entry (i, j), j <= i, at i (i + 1) / 2 + j -- every index is a compile-time
+        // constant after unrolling, so the factor lives in registers
+        float L[M * (M + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) {
+            float gij = sG[i * LAB + j], gji = sG[j * LAB + i];
+            if (i == j) { const float rd = pk0[D::oRd + i]; gij += rd; gji += rd; }
+            L[i * (i + 1) / 2 + j] = 0.5f * (gij + gji);
+          }
+        float gi[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          float d = L[j * (j + 1) / 2 + j];
+#pragma unroll
+          for (int k2 = 0; k2 < j; ++k2) d = fmaf(-L[j * (j + 1) / 2 + k2], L[j * (j + 1) / 2 + k2], d);
+          const float inv = 1.f / sqrtf(d);
+          gi[j] = inv;
+#pragma unroll
+          for (int i = j + 1; i < M; ++i) {
+            float sacc = L[i * (i + 1) / 2 + j];
+#pragma unroll
+            for (int k2 = 0; k2 < j; ++k2) sacc = fmaf(-L[i * (i + 1) / 2 + k2], L[j * (j + 1) / 2 + k2], sacc);
+            L[i * (i + 1) / 2 + j] = sacc * inv;
+          }
         }
-        __syncwarp();
+        float y[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+          float sacc = -((col < NH) ? sH[i * LAB + col] : shq[LH + i]);
+#pragma unroll
+          for (int k2 = 0; k2 < i; ++k2) sacc = fmaf(-L[i * (i + 1) / 2 + k2], y[k2], sacc);
+          y[i] = sacc * gi[i];
+        }
+#pragma unroll
+        for (int i = M - 1; i >= 0; --i) {
+          float sacc = y[i];
+#pragma unroll
+          for (int k2 = i + 1; k2 < M; ++k2) sacc = fmaf(-L[k2 * (k2 + 1) / 2 + i], y[k2], sacc);
+          y[i] = sacc * gi[i];
+        }
+        if (col < NH) {
+#pragma unroll
+          for (int i = 0; i < M; ++i) sK[i * LH + col] = y[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < M; ++i) sOK[LH + i] = y[i];
+        }
       }
+      __syncthreads();
+    } else {
+    // ---- S3: G = sym(R + G), R = diag (M = 0: H needs no correction)
+      for (int idx = tid; idx < m * m; idx += NT) {
+        const int i = idx / m, j = idx - i * m;
+        if (i <= j) {
+          float gij = sG[i * LAB + j], gji = sG[j * LAB + i];
+          if (i == j) { const float rd = pk0[D::oRd + i]; gij += rd; gji += rd; }
+          const float s = 0.5f * (gij + gji);
+          sG[i * LAB + j] = s;
+          sG[j * LAB + i] = s;
+        }
+      }
+      __syncthreads();
+      // ---- S4: Cholesky G = L L' in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
+      if (tid < 32) {
+        for (int j = 0; j < m; ++j) {
+          float d = sG[j * LAB + j];
+          for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LAB + k2], sG[j * LAB + k2], d);
+          const float inv = 1.f / sqrtf(d);
+          __syncwarp();
+          if (tid == 0) sgi[j] = inv;
+          for (int i = j + 1 + tid; i < m; i += 32) {
+            float s = sG[i * LAB + j];
+            for (int k2 = 0; k2 < j; ++k2) s = fmaf(-sG[i * LAB + k2], sG[j * LAB + k2], s);
+            sG[i * LAB + j] = s * inv;
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // ---- S5: [K k] = -G^-1 [H h]: one thread per right-hand-side column (head columns + k)
+      for (int col = tid; col <= NH; col += NT) {
+        float y[m];
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+          float s = -((col < NH) ? sH[i * LAB + col] : shq[LH + i]);
+#pragma unroll
+          for (int k2 = 0; k2 < i; ++k2) s = fmaf(-sG[i * LAB + k2], y[k2], s);
+          y[i] = s * sgi[i];
+        }
+#pragma unroll
+        for (int i = m - 1; i >= 0; --i) {
+          float s = y[i];
+#pragma unroll
+          for (int k2 = i + 1; k2 < m; ++k2) s = fmaf(-sG[k2 * LAB + i], y[k2], s);
+          y[i] = s * sgi[i];
+        }
+        if (col < NH) {
+#pragma unroll
+          for (int i = 0; i < m; ++i) sK[i * LH + col] = y[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < m; ++i) sOK[LH + i] = y[i];
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    // ---- S5: [K k] = -G^-1 [H h]: one thread per right-hand-side column (head columns + k)
-    for (int col = tid; col <= NH; col += NT) {
-      float y[m];
+    // ---- S6: XY = X + K' H on the upper tiles, p_h = q'_h + K' h
+    for (int it = vt; it < nXU + LH; it += NT) {
+      if (it < nXU) {
+        const int code = list2[it];
+        const int ri = code >> 8, cj = code & 255;
+        float acc[4][8];
 #pragma unroll
-      for (int i = 0; i < m; ++i) {
-        float s = -((col < NH) ? sH[i * LH + col] : sh[i]);
+        for (int x = 0; x < 4; ++x) {
+          const float* src = sXG + (4 * ri + x) * LAB + 8 * cj;
+          const float4 t0 = *reinterpret_cast<const float4*>(src), t1 = *reinterpret_cast<const float4*>(src + 4);
+          acc[x][0] = t0.x; acc[x][1] = t0.y; acc[x][2] = t0.z; acc[x][3] = t0.w;
+          acc[x][4] = t1.x; acc[x][5] = t1.y; acc[x][6] = t1.z; acc[x][7] = t1.w;
+        }
+        rt48_atb(acc, sK + 4 * ri, LH, sH + 8 * cj, LAB, m);
 #pragma unroll
-        for (int k2 = 0; k2 < i; ++k2) s = fmaf(-sG[i * LMB + k2], y[k2], s);
-        y[i] = s * sgi[i];
-      }
-#pragma unroll
-      for (int i = m - 1; i >= 0; --i) {
-        float s = y[i];
-#pragma unroll
-        for (int k2 = i + 1; k2 < m; ++k2) s = fmaf(-sG[k2 * LMB + i], y[k2], s);
-        y[i] = s * sgi[i];
-      }
-      if (col < NH) {
-#pragma unroll
-        for (int i = 0; i < m; ++i) sK[i * LH + col] = y[i];
+        for (int x = 0; x < 4; ++x) {
+          float* dst = sXG + (4 * ri + x) * LAB + 8 * cj;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[x][0], acc[x][1], acc[x][2], acc[x][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[x][4], acc[x][5], acc[x][6], acc[x][7]);
+        }
       } else {
-#pragma unroll
-        for (int i = 0; i < m; ++i) sOK[LH + i] = y[i];
+        const int i = it - nXU;
+        float s = shq[i];
+        for (int j = 0; j < m; ++j) s = fmaf(sK[j * LH + i], shq[LH + j], s);
+        sOK[i] = (i < NH) ? s : 0.f;
       }
     }
     __syncthreads();
-    // ---- S6: XY = X + K' H, p_h = qh + K' h
-    for (int tile = tid; tile < TH * TH + LH; tile += NT) {
-      if (tile < TH * TH) {
-        const int i0 = (tile / TH) * 8, j0 = (tile % TH) * 8;
-        float acc[8][8];
-        rt_load<8, 8>(acc, X, LH, i0, j0);
-        rt_atb<8, 8>(acc, sK, LH, i0, sH, LH, j0, m);
-        rt_store<8, 8>(X, LH, i0, j0, acc);
-      } else {
-        const int i = tile - TH * TH;
-        float s = sqh[i];
-        for (int j = 0; j < m; ++j) s = fmaf(sK[j * LH + i], sh[j], s);
-        s = (i < NH) ? s : 0.f;
-        sOK[i] = s;
-      }
-    }
-    __syncthreads();
-    // ---- S7: P_hh = sym(Q_hh + XY) over unordered pairs; p_{t} (full) for the next step
+    // ---- S7: P_hh = Q_hh + XY, upper triangle mirrored (sym(Q + A'PA + K'H) of the reference, evaluated on the
+    // upper triangle: the two halves differ by rounding only); p_t (full) for the next step
     for (int idx = tid; idx < (LH / 2 + 1) * LH; idx += NT) {
       // unordered pairs {i, (i + d) mod LH}: every pair once, consecutive lanes walk consecutive i
-      const int d = idx / LH, i = idx - d * LH;
-      int j = i + d;
-      if (j >= LH) j -= LH;
-      if ((2 * d == LH && i >= LH / 2) || i >= NH || j >= NH) continue;
-      float qij = 0.f, qji = 0.f;
-      if (i == j) { qij = pk0[D::oQd + i]; qji = qij; }
-      if (i >= 3 && i < 7 && j >= 3 && j < 7) { qij = pk0[D::oQq + (i - 3) * 4 + (j - 3)]; qji = pk0[D::oQq + (j - 3) * 4 + (i - 3)]; }
-      const float s = 0.5f * ((qij + X[i * LH + j]) + (qji + X[j * LH + i]));
-      X[i * LH + j] = s;
-      X[j * LH + i] = s;
+      const int d = idx / LH, i0 = idx - d * LH;
+      int j0 = i0 + d;
+      if (j0 >= LH) j0 -= LH;
+      if ((2 * d == LH && i0 >= LH / 2) || i0 >= NH || j0 >= NH) continue;
+      const int i = i0 < j0 ? i0 : j0, j = i0 < j0 ? j0 : i0;
+      float q = (i == j) ? pk0[D::oQd + i] : 0.f;
+      if (i >= 3 && j < 7) q = 0.5f * (pk0[D::oQq + (i - 3) * 4 + (j - 3)] + pk0[D::oQq + (j - 3) * 4 + (i - 3)]);
+      const float s = q + sXG[i * LAB + j];
+      sP[i * LH + j] = s;
+      sP[j * LH + i] = s;
     }
     for (int i = tid; i < n; i += NT) sp[i] = (i < NH) ? sOK[i] : pk0[D::oq + i];
     __syncthreads();
     fence_async_smem();
     if (tid == 0) {
-      bulk_s2g(gP + size_t(t) * D::szP, X, D::szP * sizeof(float));
+      bulk_s2g(gP + size_t(t) * D::szP, sP, D::szP * sizeof(float));
       bulk_s2g(gK + size_t(t) * D::szK, sK, D::szK * sizeof(float));
       bulk_s2g(gOK + size_t(t) * D::OKS, sOK, D::OKS * sizeof(float));
       bulk_commit();
     }
-    cur ^= 1;
     pkn ^= 1;
     if (t > 0) {
       mbar_wait(&bars[0], ph0);
@@ -500,16 +529,15 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
   float* sdx = smem + 2 * S::stage;   // [2][LN]
   float* sdu = sdx + 2 * LN;          // [LMB]
   float* sred = sdu + LMB;            // [NT / 32]
-  constexpr int oSK = 0, oSA = oSK + D::szK, oSB = oSA + D::szA, oSP = oSB + D::szB, oSPK = oSP + D::szP, oSOK = oSPK + D::PKS;
+  constexpr int oSK = 0, oSAB = oSK + D::szK, oSP = oSAB + D::szAB, oSPK = oSP + D::szP, oSOK = oSPK + D::PKS;
   auto fetch = [&](int t, int b) {   // knot t = 0..N (t == N: only P, PK, OK)
     float* st = stg[b];
     uint32_t bytes = uint32_t((D::szP + D::PKS + D::OKS) * sizeof(float));
-    if (t < N) bytes += uint32_t((D::szK + D::szA + D::szB) * sizeof(float));
+    if (t < N) bytes += uint32_t((D::szK + D::szAB) * sizeof(float));
     mbar_expect_tx(&bars[1 + b], bytes);
     if (t < N) {
       bulk_g2s(st + oSK, gK + size_t(t) * D::szK, D::szK * sizeof(float), &bars[1 + b]);
-      bulk_g2s(st + oSA, gA + size_t(t) * D::szA, D::szA * sizeof(float), &bars[1 + b]);
-      bulk_g2s(st + oSB, gB + size_t(t) * D::szB, D::szB * sizeof(float), &bars[1 + b]);
+      bulk_g2s(st + oSAB, gAB + size_t(t) * D::szAB, D::szAB * sizeof(float), &bars[1 + b]);
     }
     bulk_g2s(st + oSP, gP + size_t(t) * D::szP, D::szP * sizeof(float), &bars[1 + b]);
     bulk_g2s(st + oSPK, gPK + size_t(t) * D::PKS, D::PKS * sizeof(float), &bars[1 + b]);
@@ -559,22 +587,13 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
       for (int row0 = 0; row0 < n; row0 += NT / PX) {
         const int row = row0 + tid / PX, part = tid % PX;
         float s = 0.f;
-        if (row < NH) {
+        if (row < NH)
           for (int j = part; j < NH; j += PX) s = fmaf(P[row * LH + j], dx[j], s);
-        }
 #pragma unroll
         for (int o = PX / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (row < n && part == 0) {
-          if (row < NH) {
-            s += st[oSOK + row];
-          } else {
-            s = fmaf(pk[D::oQd + row], dx[row], pk[D::oq + row]);
-            if (NCONE > 0 && row >= D::cone0) {
-              const int blk = (row - D::cone0) / 3, k0 = D::cone0 + 3 * blk, ri = row - k0;
-              const float* cb = pk + D::oQc + 9 * blk + 3 * ri;
-              s = fmaf(cb[0], dx[k0], fmaf(cb[1], dx[k0 + 1], fmaf(cb[2], dx[k0 + 2], s)));
-            }
-          }
+          if (row < NH) s += st[oSOK + row];
+          else s = pk[D::oq + row] + lq3_tail_row<D>(pk, row, dx, 1);
           gdV[size_t(t) * n + row] = s;
           gdX[size_t(t) * n + row] = dx[row];
           slope_acc = fmaf(pk[D::oq + row], dx[row], slope_acc);
@@ -586,15 +605,14 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
     // dx+ = A dx_h + B du + c_{t+1}: c_{t+1} sits in the OTHER stage's PK block (knot t+1, already requested)
     mbar_wait(&bars[1 + (b ^ 1)], phs[b ^ 1]);   // peek: do not flip the phase, the next iteration waits again
     {
-      const float* Am = st + oSA;
-      const float* Bm = st + oSB;
+      const float* AB = st + oSAB;
       const float* cn = stg[b ^ 1] + oSPK + D::oc;
       for (int row0 = 0; row0 < n; row0 += NT / PX) {
         const int row = row0 + tid / PX, part = tid % PX;
         float s = 0.f;
         if (row < n) {
-          for (int j = part; j < NH; j += PX) s = fmaf(Am[row * LH + j], dx[j], s);
-          for (int j = part; j < m; j += PX) s = fmaf(Bm[row * LMB + j], sdu[j], s);
+          for (int j = part; j < NH; j += PX) s = fmaf(AB[row * LAB + j], dx[j], s);
+          for (int j = part; j < m; j += PX) s = fmaf(AB[row * LAB + LH + j], sdu[j], s);
         }
 #pragma unroll
         for (int o = PX / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -19,12 +19,14 @@ struct ModelIO {
 
 struct LinOut {
   float *A, *B, *Q, *R, *M, *q, *r, *c, *cost;
-  // Row strides of A / B (dense: n / m).  Structured mode (compact != 0; lq3.cuh): A is [N][n][ldA] with only the
-  // leading 13 + 2 nj columns live (ldA = that padded to 8), B is [N][n][ldB] (m padded to 4), Q / R / M / q / r are
-  // not written; instead every knot gets one packed block PK[t] of `pks` floats:
+  // Row strides of A / B (dense: n / m).  Structured mode (compact != 0; lq3.cuh): A and B share one block
+  // [A_t | B_t] of row stride ldA = ldB per knot (B points at its first column); only the leading 13 + 2 nj columns of
+  // A are live, followed by padA zero columns, B by padB zero columns; Q / R / M / q / r are not written; instead every
+  // knot gets one packed block PK[t] of `pks` floats:
   //   diag(Q_t) @oQd | q_t @oq | c_t @oc | 4x4 quaternion block of Q_t @oQq | 3x3 cone blocks @oQc | diag(R_t) @oRd | r_t @oR
   // (the layout of Lq3Dims).  c is still written densely as well (the line search reads it).
   int ldA, ldB;
+  int padA, padB;
   int compact;
   float* PK;
   int pks, oQd, oq, oc, oQq, oQc, oRd, oR;

@@ -98,9 +98,9 @@ bool lq3_supported(const Lq3Layout& s) {
 }
 int dispatch_lq3(const Lq3Layout& s, const Lq3Args& a, cudaStream_t st) {
   cudaError_t err = cudaErrorInvalidValue;
-  if (s.nh == 37 && s.m == 12) err = launch_lq3<37, 24, 12, 4, 64>(a, st);
-  else if (s.nh == 51 && s.m == 19) err = launch_lq3<51, 24, 19, 0, 64>(a, st);
-  else if (s.nh == 57 && s.m == 46) err = launch_lq3<57, 24, 46, 0, 64>(a, st);
+  if (s.nh == 37 && s.m == 12) err = launch_lq3<37, 24, 12, 4, 128>(a, st);
+  else if (s.nh == 51 && s.m == 19) err = launch_lq3<51, 24, 19, 0, 128>(a, st);
+  else if (s.nh == 57 && s.m == 46) err = launch_lq3<57, 24, 46, 0, 128>(a, st);
   else return MPXB_EUNSUPPORTED;
   return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
@@ -279,9 +279,10 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     float* Vn = to_user ? V : ws + L.Vt;
     ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
     LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost,
-              n, m, 0, nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+              n, m, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
     if (structured) {
-      lo.A = ws + L.Ac; lo.B = ws + L.Bc; lo.ldA = s3.LH; lo.ldB = s3.LMB; lo.compact = 1; lo.PK = ws + L.PK;
+      lo.A = ws + L.ABc; lo.B = ws + L.ABc + s3.LH; lo.ldA = s3.LAB; lo.ldB = s3.LAB; lo.compact = 1; lo.PK = ws + L.PK;
+      lo.padA = s3.LH - s3.nh; lo.padB = s3.LM8 - s3.m;
       lo.pks = s3.PKS; lo.oQd = s3.oQd; lo.oq = s3.oq; lo.oc = s3.oc; lo.oQq = s3.oQq; lo.oQc = s3.oQc; lo.oRd = s3.oRd;
       lo.oR = s3.oR;
     }
@@ -311,7 +312,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
               d.kind == MPXB_KIND_SRBD ? 0 : 13 + 2 * d.n_joints};
     int rc;
     if (structured) {
-      Lq3Args l3{E, N, ws + L.Ac, ws + L.Bc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc, ws + L.dX, ws + L.dU, ws + L.dV,
+      Lq3Args l3{E, N, ws + L.ABc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc, ws + L.dX, ws + L.dU, ws + L.dV,
                  ws + L.slope, done};
       rc = dispatch_lq3(s3, l3, st);
     } else {
@@ -379,7 +380,7 @@ int mpxb_workspace_expand(const mpxb_model* mdl, void* stream, int E, int lq_mod
   DeviceGuard guard(mdl->device);
   const WsLayout L = layout_of(mdl, E, lq_mode);
   float* ws = static_cast<float*>(workspace);
-  ExpandArgs a{E, mdl->desc.N, mdl->s3, ws + L.Ac, ws + L.Bc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc,
+  ExpandArgs a{E, mdl->desc.N, mdl->s3, ws + L.ABc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc,
                ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.K, ws + L.k, ws + L.P, ws + L.p};
   lq3_expand_kernel<<<E * (mdl->desc.N + 1), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;

@@ -14,8 +14,8 @@ namespace mpxb {
 struct WsLayout {
   size_t A, B, Q, R, M, q, r, c, K, k, P, p, dX, dU, dV, cost, ls_theta, ls_phi, slope, g, Xt, Ut, Vt, last_cost,
       done, scan, theta_k, phi_k, need, ls_vc, vc_k, dv2, dvc, th_part, ph_part, vc_part, need_count,
-      // structured path (lq3.cuh): compact A / B, packed knot blocks, compact K / P, packed p | k
-      Ac, Bc, PK, Kc, Pc, OKc, total;
+      // structured path (lq3.cuh): [A | B] blocks, packed knot blocks, compact K / P, packed p | k
+      ABc, PK, Kc, Pc, OKc, total;
 };
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
@@ -62,10 +62,9 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats, cons
   L.ph_part = take(e * NALPHA * (N + 1));
   L.vc_part = take(e * NALPHA * (N + 1));
   L.need_count = take(1);  // int32
-  L.Ac = L.Bc = L.PK = L.Kc = L.Pc = L.OKc = 0;
+  L.ABc = L.PK = L.Kc = L.Pc = L.OKc = 0;
   if (s3) {
-    L.Ac = take(e * N * s3->szA);
-    L.Bc = take(e * N * s3->szB);
+    L.ABc = take(e * N * s3->szAB);
     L.PK = take(e * (N + 1) * s3->PKS);
     L.Kc = take(e * N * s3->szK);
     L.Pc = take(e * (N + 1) * s3->szP);
@@ -218,7 +217,7 @@ __global__ void shift_extract_kernel(int E, int N, int n, int m, int nj, int shi
 struct ExpandArgs {
   int E, N;
   Lq3Layout s;
-  const float *Ac, *Bc, *PK, *Kc, *Pc, *OKc;
+  const float *ABc, *PK, *Kc, *Pc, *OKc;
   float *A, *B, *Q, *R, *M, *q, *r, *K, *k, *P, *p;
 };
 __global__ void lq3_expand_kernel(ExpandArgs a) {
@@ -252,8 +251,8 @@ __global__ void lq3_expand_kernel(ExpandArgs a) {
     a.p[(size_t(e) * (N + 1) + t) * n + i] = (i < nh) ? ok[i] : pk[s.oq + i];
   }
   if (t == N) return;
-  const float* Ac = a.Ac + (size_t(e) * N + t) * s.szA;
-  const float* Bc = a.Bc + (size_t(e) * N + t) * s.szB;
+  const float* Ac = a.ABc + (size_t(e) * N + t) * s.szAB;
+  const float* Bc = Ac + s.LH;
   const float* Kc = a.Kc + (size_t(e) * N + t) * s.szK;
   float* A = a.A + (size_t(e) * N + t) * n * n;
   float* B = a.B + (size_t(e) * N + t) * n * m;
@@ -262,11 +261,11 @@ __global__ void lq3_expand_kernel(ExpandArgs a) {
   float* K = a.K + (size_t(e) * N + t) * m * n;
   for (int idx = tid; idx < n * n; idx += NT) {
     const int i = idx / n, j = idx - i * n;
-    A[idx] = (j < nh) ? Ac[i * s.LH + j] : 0.f;
+    A[idx] = (j < nh) ? Ac[i * s.LAB + j] : 0.f;
   }
   for (int idx = tid; idx < n * m; idx += NT) {
     const int i = idx / m, j = idx - i * m;
-    B[idx] = Bc[i * s.LMB + j];
+    B[idx] = Bc[i * s.LAB + j];
     M[idx] = 0.f;
   }
   for (int idx = tid; idx < m * m; idx += NT) {

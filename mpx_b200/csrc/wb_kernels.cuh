@@ -638,12 +638,12 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       satv[is_u ? n + tid - NDS : tid] = atv;
     }
     // the foot / GRF tail of the state does not enter the dynamics (structured mode: only the pad columns exist)
-    const int ntail = o.ldA - NDS;
+    const int ntail = o.compact ? o.padA : n - NDS;
     for (int idx = tid; idx < n * ntail; idx += NT) {
       const int i = idx / ntail, j = NDS + idx - i * ntail;
       A[i * o.ldA + j] = 0.f;
     }
-    const int nbpad = o.ldB - m;
+    const int nbpad = o.compact ? o.padB : 0;
     for (int idx = tid; idx < n * nbpad; idx += NT) {
       const int i = idx / nbpad, j = m + idx - i * nbpad;
       B[i * o.ldB + j] = 0.f;

@@ -17,8 +17,12 @@ for r in data0:  # the page lists every instruction once per collection pass: ke
         data.append(r)
 td = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath("mpx_b200/libmpxb.so")], cwd=td, capture_output=True)
-cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(td, cub)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cub in sorted(f for f in os.listdir(td) if f.endswith(".cubin")):  # one cubin per translation unit
+    d = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(td, cub)], capture_output=True, text=True).stdout.splitlines()
+    if any(".text." in l and mangled in l for l in d):
+        dis = d
+        break
 # find the .text section of the kernel
 start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and mangled in l or (l.strip().startswith(".section") and ".text." in l and mangled in l))
 lines = []
