@@ -8,7 +8,9 @@ A "step" is one pass of the hot path over one batch of synthetic robot states: o
 (evaluate + linearise/quadratise + LQ solve + 11-alpha filter line search) for every environment, followed by
 the warm-start shift, in closed loop on the model (x0 <- X[shift]).  Workload at N=1: Go2 whole-body MPC,
 1024 environments per GPU (BASELINE.json configs[2]); with N>1 every rank owns its own 1024-environment slice
-(weak scaling, no collective on the solve path, one final gather of the controls).
+(weak scaling, no collective on the solve path; the end-to-end tick ends with the NCCL gather of the controls).
+The same line carries, under "strong", the north-star split: Go2 x4096 and H1 x4096 (configs[4]) sharded as
+4096 / N environments per GPU.
 """
 import argparse
 import importlib
@@ -112,38 +114,31 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def _cpu_solve_worker(args):
-    """One restated-reference `optimizers.mpc` call (float32 torch oracle) for one environment."""
-    robot, seed = args
+def cpu_arm(robot, steps, warmup, envs, seed=1000):
+    """Times the restated reference on the host cores: each step = ONE batched `optimizers.mpc` call over `envs`
+    environments, float32, evaluated by oracle/batched.py the way the reference evaluates it -- vmap over knots inside
+    vmap over environments (examples/multi_env.py:46-49), one process, every core through torch's intra-op threads.
+    Returns (solves/s, ms per step, threads used)."""
     import torch
-    torch.set_num_threads(1)
+    from oracle.batched import BatchedProblem
     from oracle.problems import Problem, synthetic_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
-    key = ("pr", robot)
-    if key not in _cpu_solve_worker.__dict__:
-        _cpu_solve_worker.__dict__[key] = Problem(cfg, dtype=torch.float32)
-    pr = _cpu_solve_worker.__dict__[key]
-    inp = synthetic_inputs(pr, 1, seed=seed)
+    bp = BatchedProblem(Problem(cfg, dtype=torch.float32))
+    inp = synthetic_inputs(bp.pr, envs, seed=seed)
+    args = (inp["reference"], inp["parameter"], inp["x0"])
+    X, U, V = inp["X0"], inp["U0"], inp["V0"]
+    lm = robot != "srbd"
+    for _ in range(warmup):
+        bp.mpc(lm, *args, X, U, V)
     t0 = time.perf_counter()
-    pr.mpc(True, inp["reference"][0], inp["parameter"][0], inp["x0"][0], inp["X0"][0], inp["U0"][0], inp["V0"][0])
-    return time.perf_counter() - t0
-
-
-def cpu_arm(robot, steps, warmup, cores):
-    """Times the oracle port on the host cores: each step = `cores` independent solves, one per process."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        seed = 1000
-        for _ in range(warmup):
-            pool.map(_cpu_solve_worker, [(robot, seed + i) for i in range(cores)])
-            seed += cores
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            pool.map(_cpu_solve_worker, [(robot, seed + i) for i in range(cores)])
-            seed += cores
-        dt = time.perf_counter() - t0
-    return cores * steps / dt, dt / steps * 1e3
+    for _ in range(steps):
+        # closed loop on the same batch: the next call starts from this call's iterate (no shift: the CPU arm times
+        # the solve, which is >99.9 % of a tick)
+        X, U, V = (t.numpy() for t in bp.mpc(lm, *args, X, U, V))
+    dt = time.perf_counter() - t0
+    return envs * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
 def run_reference(args):
@@ -151,18 +146,18 @@ def run_reference(args):
     if rank != 0:
         return
     robot, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    # bounded sample: the pure-Python/torch restatement needs ~10-20 s per whole-body solve per core, so the
-    # number of timed steps is capped to keep the run within minutes (stated in `sample`)
+    envs = args.ref_envs
+    # bounded sample: the timed steps are capped so that the run ends within minutes (stated in `sample`)
     steps = max(1, min(args.steps, args.ref_max_steps))
     warmup = min(args.warmup, 1)
-    value, ms = cpu_arm(robot, steps, warmup, cores)
-    sample = (f"{cores} independent solves per step (one per process), {steps} timed steps after {warmup} warm-up; "
-              f"float32 torch restatement of the reference (JAX/MJX not installable here)")
+    value, ms, cores = cpu_arm(robot, steps, warmup, envs)
+    sample = (f"{envs} environments per step in one batched call (the native arm runs {args.envs} per GPU), {steps} timed "
+              f"steps after {warmup} warm-up; float32 torch restatement of the reference vectorised over environments and "
+              f"knots like jax.vmap (JAX / MJX are not installable in this image)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "robot": robot, "envs_per_step": cores},
+            "config": {"workload": desc, "robot": robot, "envs_per_step": envs},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -256,13 +251,88 @@ def latency_leg(dev, ticks=1000, warm=20):
 
 
 # --------------------------------------------------------------------------------------------- native arm
+LQ_NAMES = {0: "sequential", 1: "scan", 2: "scan-serial", 3: "scan-parallel"}
+
+
+class Loop:
+    """One closed-loop workload on one GPU: wrapper, pre-generated input tape resident in HBM, and the timed step."""
+
+    def __init__(self, args, robot, E, K, n_warm, rank, dev, lm, horizon=0):
+        import torch
+        from mpx_b200.utils.mpc_wrapper import BatchedMPCControllerWrapper
+        from mpx_b200.utils.mpc_wrapper_srbd import BatchedMPCControllerWrapper as SrbdWrapper
+        cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
+        if horizon and horizon != cfg.N:
+            # horizon sweep (BASELINE configs[3]): the same config with N replaced; every kernel takes N at run time
+            from types import SimpleNamespace
+            cfg = SimpleNamespace(**{k: getattr(cfg, k) for k in dir(cfg) if not k.startswith("__")})
+            cfg.N = int(horizon)
+        self.cfg, self.E, self.K, self.dev, self.robot = cfg, E, K, dev, robot
+        self.srbd = srbd = robot == "srbd"
+        st = self.st = synthetic_states(cfg, E, seed=rank)
+        T = self.T = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
+        N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
+        if srbd:
+            wrap = SrbdWrapper(cfg, E, device=dev)
+            yaw = st["yaw"]
+            Ry = np.stack([np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw], 1), np.stack([np.sin(yaw), np.cos(yaw), 0 * yaw], 1),
+                           np.stack([0 * yaw, 0 * yaw, 1 + 0 * yaw], 1)], 1)
+            base = np.concatenate([st["qpos"][:, :2], np.zeros((E, 1))], 1)
+            feet = T((base[:, None, :] + np.einsum("eij,fj->efi", Ry, np.asarray(cfg.p_legs0).reshape(nc, 3))).reshape(E, -1))
+            x0 = T(np.concatenate([st["qpos"][:, :7], st["qvel"][:, :6]], 1))
+            wrap.contact_time = T(st["timer"])
+            wrap.liftoff = feet.clone()
+        else:
+            wrap = BatchedMPCControllerWrapper(cfg, E, limited_memory=lm, device=dev)
+            self.qpos, self.qvel = T(st["qpos"]), T(st["qvel"])
+            feet = wrap.foot_positions(self.qpos)
+            data = wrap.reset(wrap.make_data(), self.qpos, self.qvel, feet)
+            data = data.replace(contact_time=T(st["timer"]))
+            x0 = data.X0[:, 0, :].clone()
+        self.wrap, self.solver, self.feet = wrap, wrap._solver, feet
+        self.Wt, self.u_ref = T(cfg.W), T(cfg.u_ref)
+        self.shift = shift = int(1 / (cfg.dt * cfg.mpc_frequency))
+        # ---- input tape: the real closed loop (gait timer + reference generator + solve + shift, x0 <- X[shift]) is
+        # run once, untimed, for n_warm + K ticks and its per-tick solve inputs (reference, parameter, x0) are kept in
+        # HBM.  The timed loop replays the tape through the solve + shift kernels only; every kernel is deterministic,
+        # so the replay reproduces the closed-loop iterates exactly.
+        tape = []
+        if srbd:
+            for _ in range(n_warm + K):
+                wrap.run(x0, T(st["cmd"]), feet, torch.ones(E, nc, device=dev))
+                tape.append((wrap.reference, wrap.parameter, x0))
+                x0 = wrap.X[:, shift, :].clone()
+                feet = wrap.parameter[:, 0, 4:].clone()
+            self.x_init = tape[0][2]
+            X0 = wrap.initial_state.repeat(E, N + 1, 1).contiguous()
+        else:
+            cmd = T(st["cmd"])
+            d = data
+            for _ in range(n_warm + K):
+                d, _ = wrap.run(d, x0, cmd)
+                tape.append((wrap.reference, wrap.parameter, x0))
+                x0 = wrap.X[:, shift, :].clone()
+            self.x_init = tape[0][2]
+            X0 = self.x_init[:, None, :].repeat(1, N + 1, 1).contiguous()
+        self.tape, self.pos = tape, 0
+        self.X0, self.U0 = X0, self.u_ref.repeat(E, N, 1).contiguous()
+        self.V0 = torch.zeros(E, N + 1, n, device=dev)
+        self.X, self.U, self.V = torch.empty_like(self.X0), torch.empty_like(self.U0), torch.empty_like(self.V0)
+        self.launches_per_step = self.solver.launches_per_call + 1
+
+    def step(self):
+        reference, parameter, x0c = self.tape[self.pos]
+        self.pos += 1
+        self.solver.solve(reference, parameter, self.Wt, x0c, self.X0, self.U0, self.V0, out=(self.X, self.U, self.V))
+        self.solver.shift_extract(self.X, self.U, self.V, x0c, self.u_ref, self.X0, self.U0, self.V0, self.shift, want_cmd=False)
+
+
 def run_native(args):
     import ctypes as C
+    import socket
     import torch
     import torch.distributed as dist
     from mpx_b200 import _lib
-    from mpx_b200.utils.mpc_wrapper import BatchedMPCControllerWrapper
-    from mpx_b200.utils.mpc_wrapper_srbd import BatchedMPCControllerWrapper as SrbdWrapper
     from mpx_b200.utils.sharding import gather_controls, max_over_ranks
 
     rank = int(os.environ.get("RANK", "0"))
@@ -272,23 +342,18 @@ def run_native(args):
         raise RuntimeError("bench.py native arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    nccl_log = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION / INFO print to stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("MPXB_NCCL_DEBUG", "WARN")
+        # stdout carries the one JSON line only: NCCL's INFO log goes to one file per rank and is echoed to stderr below
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "mpxb_nccl_%h_%p.log"))
+        nccl_log = os.environ["NCCL_DEBUG_FILE"].replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
         dist.init_process_group("nccl", device_id=dev)
     robot, desc = WORKLOADS[args.workload]
-    cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
-    if args.horizon and args.horizon != cfg.N:
-        # horizon sweep (BASELINE configs[3]): the same config with N replaced; every kernel takes N at run time
-        from types import SimpleNamespace
-        cfg = SimpleNamespace(**{k: getattr(cfg, k) for k in dir(cfg) if not k.startswith("__")})
-        cfg.N = int(args.horizon)
     E, K, Wm = args.envs, args.steps, args.warmup
     srbd = robot == "srbd"
     lib = _lib.lib()
-    st = synthetic_states(cfg, E, seed=rank)
-    T = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
-    N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
     # limited_memory as the reference's examples pass it: True for the batched whole-body runs (multi_env.py:44), the
     # default False for the single-instance controllers and the SRBD wrapper; the wrappers then bind the LQ kernel
     # that is fastest for the shape (optimizers.wrapper_lq_mode); --scan binds the associative scan literally
@@ -297,63 +362,11 @@ def run_native(args):
         if args.scan_schedule:
             os.environ["MPXB_SCAN_SCHEDULE"] = args.scan_schedule
         os.environ["MPXB_LQ"] = "scan"  # bind the associative-scan kernel literally (wrappers default to the sequential one)
-
-    if srbd:
-        wrap = SrbdWrapper(cfg, E, device=dev)
-        solver = wrap._solver
-        yaw = st["yaw"]
-        Ry = np.stack([np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw], 1), np.stack([np.sin(yaw), np.cos(yaw), 0 * yaw], 1),
-                       np.stack([0 * yaw, 0 * yaw, 1 + 0 * yaw], 1)], 1)
-        base = np.concatenate([st["qpos"][:, :2], np.zeros((E, 1))], 1)
-        feet = T((base[:, None, :] + np.einsum("eij,fj->efi", Ry, np.asarray(cfg.p_legs0).reshape(nc, 3))).reshape(E, -1))
-        x0 = T(np.concatenate([st["qpos"][:, :7], st["qvel"][:, :6]], 1))
-        wrap.contact_time = T(st["timer"])
-        wrap.liftoff = feet.clone()
-    else:
-        wrap = BatchedMPCControllerWrapper(cfg, E, limited_memory=lm, device=dev)
-        solver = wrap._solver
-        qpos, qvel = T(st["qpos"]), T(st["qvel"])
-        feet = wrap.foot_positions(qpos)
-        data = wrap.reset(wrap.make_data(), qpos, qvel, feet)
-        data = data.replace(contact_time=T(st["timer"]))
-        x0 = data.X0[:, 0, :].clone()
-    Wt = T(cfg.W)
-    u_ref = T(cfg.u_ref)
-    shift = int(1 / (cfg.dt * cfg.mpc_frequency))
     n_warm = max(Wm, 3)
-    # ---- input tape: the real closed loop (gait timer + reference generator + solve + shift, x0 <- X[shift]) is run
-    # once, untimed, for n_warm + K ticks and its per-tick solve inputs (reference, parameter, x0) are kept in HBM.
-    # The timed loop replays the tape through the solve + shift kernels only; every kernel is deterministic, so the
-    # replay reproduces the closed-loop iterates exactly.
-    tape = []
-    if srbd:
-        for _ in range(n_warm + K):
-            wrap.run(x0, T(st["cmd"]), feet, torch.ones(E, nc, device=dev))
-            tape.append((wrap.reference, wrap.parameter, x0))
-            x0 = wrap.X[:, shift, :].clone()
-            feet = wrap.parameter[:, 0, 4:].clone()
-        x_init = tape[0][2]
-        X0 = wrap.initial_state.repeat(E, N + 1, 1).contiguous()
-    else:
-        cmd = T(st["cmd"])
-        d = data
-        for _ in range(n_warm + K):
-            d, _ = wrap.run(d, x0, cmd)
-            tape.append((wrap.reference, wrap.parameter, x0))
-            x0 = wrap.X[:, shift, :].clone()
-        x_init = tape[0][2]
-        X0 = x_init[:, None, :].repeat(1, N + 1, 1).contiguous()
-    U0 = u_ref.repeat(E, N, 1).contiguous()
-    V0 = torch.zeros(E, N + 1, n, device=dev)
-    X, U, V = torch.empty_like(X0), torch.empty_like(U0), torch.empty_like(V0)
-    tape_pos = [0]
-
-    def step():
-        reference, parameter, x0c = tape[tape_pos[0]]
-        tape_pos[0] += 1
-        solver.solve(reference, parameter, Wt, x0c, X0, U0, V0, out=(X, U, V))
-        solver.shift_extract(X, U, V, x0c, u_ref, X0, U0, V0, shift, want_cmd=False)
-    launches_per_step = solver.launches_per_call + 1
+    loop = Loop(args, robot, E, K, n_warm, rank, dev, lm, args.horizon)
+    cfg, solver, wrap, st, T = loop.cfg, loop.solver, loop.wrap, loop.st, loop.T
+    N, n, m, nj, nc = cfg.N, cfg.n, cfg.m, cfg.n_joints, cfg.n_contact
+    shift = loop.shift
 
     def barrier():
         if world > 1:
@@ -367,7 +380,7 @@ def run_native(args):
     while time.perf_counter() - t_pre < args.prewarm_s:
         fp32_peak = max(fp32_peak, float(lib.mpxb_fp32_peak_tflops(None, 2048)))
     for _ in range(n_warm):
-        step()
+        loop.step()
     prof = C.c_void_p()
     _lib.check(lib.mpxb_profile_create(K, C.byref(prof)), "mpxb_profile_create")
     _lib.check(lib.mpxb_profile_attach(solver.handle, prof), "mpxb_profile_attach")
@@ -376,7 +389,7 @@ def run_native(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(K):
-        step()
+        loop.step()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -386,25 +399,40 @@ def run_native(args):
     _lib.check(lib.mpxb_profile_read(prof, C.byref(kms), C.byref(ncalls)), "mpxb_profile_read")
     lib.mpxb_profile_attach(solver.handle, None)
     lib.mpxb_profile_destroy(prof)
-    nonfinite_envs = int((~torch.isfinite(X).flatten(1).all(1)).sum().item())
+    nonfinite_envs = int((~torch.isfinite(loop.X).flatten(1).all(1)).sum().item())
     alpha_hist = torch.bincount(solver.alpha_index.to(torch.int64), minlength=11).tolist()
     ms_total = max_over_ranks(ms_total, device=dev)
 
-    # ---- end to end through the wrapper API with HOST buffers (H2D of x0 / command, D2H of the torques every step)
-    e2e = None
+    # ---- end to end through the wrapper API with HOST buffers: H2D of x0 / command, the whole tick, the NCCL gather of
+    # the controls onto rank 0 (N > 1; north_star: "only a final NCCL gather of controls") and the D2H read of the
+    # torques, every step
+    gather_ms = None
     if not srbd:
         x0_h = torch.empty(E, n, dtype=torch.float32).pin_memory()
         cmd_h = torch.as_tensor(st["cmd"]).pin_memory()
-        tau_h = torch.empty(E, nj, dtype=torch.float32).pin_memory()
-        x0_h.copy_(x_init.cpu())
-        d2 = wrap.reset(wrap.make_data(), qpos, qvel, feet).replace(contact_time=T(st["timer"]))
+        tau_h = torch.empty(E * (world if rank == 0 else 1), nj, dtype=torch.float32).pin_memory()
+        x0_h.copy_(loop.x_init.cpu())
+        d2 = wrap.reset(wrap.make_data(), loop.qpos, loop.qvel, loop.feet).replace(contact_time=T(st["timer"]))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_acc = []
 
-        def tick(d):
+        def tick(d, timed=False):
             xd = x0_h.to(dev, non_blocking=True)
             cd = cmd_h.to(dev, non_blocking=True)
             d, tau = wrap.run(d, xd, cd)
-            tau_h.copy_(tau, non_blocking=True)
+            if world > 1:
+                if timed:
+                    g0.record()
+                tau_all = gather_controls(tau.contiguous(), n_env_total=E * world, dst=0)   # same stream as the solve
+                if timed:
+                    g1.record()
+                if rank == 0:
+                    tau_h.copy_(tau_all, non_blocking=True)
+            else:
+                tau_h.copy_(tau, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()     # the caller reads tau
+            if timed and world > 1:
+                gather_acc.append(g0.elapsed_time(g1))
             x0_h.copy_(wrap.X[:, shift, :], non_blocking=True)   # simulator stand-in: next measured state (not counted)
             return d
         for _ in range(max(Wm, 3)):
@@ -413,20 +441,23 @@ def run_native(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(K):
-            d2 = tick(d2)
+            d2 = tick(d2, True)
         e1.record()
         barrier()
         t_e2e = max_over_ranks(e0.elapsed_time(e1), device=dev)
+        if gather_acc:
+            gather_ms = max_over_ranks(float(np.mean(gather_acc)), device=dev)
         e2e = {"value": E * world * K / (t_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(E * (n + 7) * 4), "d2h_bytes_per_step": int(E * nj * 4),
-               "ms_per_step": t_e2e / K,
-               "api": "BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
-
+               "h2d_bytes_per_step": int(E * (n + 7) * 4), "d2h_bytes_per_step": int(E * (world if world > 1 else 1) * nj * 4),
+               "ms_per_step": t_e2e / K, "gather_ms_per_step": gather_ms,
+               "api": "BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift)"
+                      + (", NCCL gather of tau [E/N, nj] onto rank 0 on the solve stream" if world > 1 else "")
+                      + ", pinned host buffers"}
     else:
         x0_h = torch.empty(E, n, dtype=torch.float32).pin_memory()
-        x0_h.copy_(x_init.cpu())
+        x0_h.copy_(loop.x_init.cpu())
         cmd_h = torch.as_tensor(st["cmd"]).pin_memory()
-        feet_h = tape[0][1][:, 0, 4:].cpu().pin_memory()
+        feet_h = loop.tape[0][1][:, 0, 4:].cpu().pin_memory()
         con_h = torch.ones(E, nc).pin_memory()
         grf_h = torch.empty(E, 3 * nc, dtype=torch.float32).pin_memory()
         wrap.reset(verbose=False)
@@ -455,9 +486,40 @@ def run_native(args):
                "ms_per_step": t_e2e / K,
                "api": "mpc_wrapper_srbd.BatchedMPCControllerWrapper.run (gait timer + reference generator + solve + shift), pinned host buffers"}
 
-    # final gather of the controls (the only collective; north_star), outside the timed solve path
-    if world > 1:
-        gather_controls(U[:, 0, :nj].contiguous(), n_env_total=E * world, dst=0)
+    # ---- strong scaling (north_star; BASELINE configs[4]): a FIXED batch of `strong_envs` environments sharded over
+    # the ranks, 4096 / N per GPU, for Go2 and H1; device-timed like the main line, max over ranks
+    strong = None
+    if not args.no_strong and args.workload == "go2_wb" and not args.scan and args.strong_envs % world == 0:
+        strong = {"total_envs": args.strong_envs, "envs_per_gpu": args.strong_envs // world, "steps": max(4, K // 2)}
+        del loop.tape
+        for rb in ("go2", "h1"):
+            Ks = strong["steps"]
+            lp = Loop(args, rb, args.strong_envs // world, Ks, 3, rank, dev, True)
+            for _ in range(3):
+                lp.step()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(Ks):
+                lp.step()
+            s1.record()
+            barrier()
+            ms = max_over_ranks(s0.elapsed_time(s1), device=dev) / Ks
+            bad = torch.tensor([float((~torch.isfinite(lp.X).flatten(1).all(1)).sum().item())], device=dev)
+            if world > 1:
+                dist.all_reduce(bad)
+            strong[rb] = {"ms_per_step": ms, "value": args.strong_envs / (ms * 1e-3), "unit": UNIT,
+                          "nonfinite_envs": int(bad.item())}
+            del lp
+            torch.cuda.empty_cache()
+
+    if nccl_log and os.path.exists(nccl_log):
+        # the communicator's own account of itself (ranks, transports, NVLS), for whoever reads the run's stderr
+        keep = ("nranks", "Init COMPLETE", "NVLS", "Connected all", "comm 0x")
+        for ln in open(nccl_log, errors="replace"):
+            if any(k in ln for k in keep):
+                sys.stderr.write(ln)
+        sys.stderr.flush()
 
     if rank == 0:
         peaks = {}
@@ -471,49 +533,58 @@ def run_native(args):
         dom = max(kernel_ms, key=kernel_ms.get)
         flq = f_lqr(n, m, N) * E
         blq = lq_bytes(n, m, N) * E
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr.get(args.workload, {}).get("lq_solve_dram_bytes_per_launch")
-        except Exception:
-            pass
+        step_s = ms_total / K * 1e-3
         lq_s = kernel_ms["lq_solve"] * 1e-3
-        lq_name = {_lib.LQ_SEQUENTIAL: "sequential", _lib.LQ_SCAN: "scan", _lib.LQ_SCAN_SERIAL: "scan-serial",
-                   _lib.LQ_SCAN_PARALLEL: "scan-parallel"}[solver.lq_mode]
+        lq_name = LQ_NAMES[solver.lq_mode]
         if solver.lq_mode == _lib.LQ_SCAN:
             lq_name = "scan-parallel" if E <= 64 else "scan-serial"
-        roofline = {"kernel": {"sequential": "lq_seq_kernel", "scan-serial": "lq_scan_kernel"}.get(lq_name, "pscan_init + pscan_combine x levels + pscan_gains + pscan_rollout"), "bound": "fp32",
-                    "achieved": flq / lq_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": flq / lq_s / 1e12 / fp32_peak, "traffic": traffic,
+        structured = bool(getattr(solver, "_structured", False)) and lq_name == "sequential"
+        lq_kernel = "lq3_kernel" if structured else {"sequential": "lq_seq_kernel", "scan-serial": "lq_scan_kernel"}.get(
+            lq_name, "pscan_init + pscan_combine x levels + pscan_gains + pscan_rollout")
+        # DRAM traffic per launch of the two largest kernels from the newest ncu --set full capture of this command
+        # (profiles/traffic.json names the capture); the run itself cannot read DRAM counters
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+            traffic = tr.get(dom + "_dram_bytes_per_launch")
+            traffic_src = tr.get("capture")
+        except Exception:
+            tr = {}
+        # achieved = F_lqr x solves/s over the WHOLE step (linearise + LQ + line search + shift) against
+        # the FP32 FFMA peak measured in this run; the LQ kernel's own fraction and every kernel's share sit beside it
+        roofline = {"bound": "fp32", "achieved": flq / step_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": flq / step_s / 1e12 / fp32_peak, "traffic": traffic,
+                    "scope": "whole step: F_lqr x solves per step / step time (SURVEY.md 8d)",
+                    "traffic_of": dom, "traffic_source": traffic_src,
                     "peak_source": "FP32 FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                    "algorithmic": f"F_lqr(n={n},m={m},N={N}) = {f_lqr(n, m, N) / 1e6:.2f} MFLOP per solve x {E} solves per launch",
-                    "hbm": {"achieved": blq / lq_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                            "frac": (blq / lq_s / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
-                            "algorithmic": f"{lq_bytes(n, m, N) / 1e6:.3f} MB per solve (LQ data read once + outputs written once)"},
-                    "whole_step": {"achieved": flq / (ms_total / K * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                   "frac": flq / (ms_total / K * 1e-3) / 1e12 / fp32_peak,
-                                   "note": "SURVEY.md 8(d): F_lqr x solves/s / FP32 peak over the whole tick (linearise + LQ + line search + shift)"},
-                    "kernel_ms": kernel_ms, "dominant_kernel": dom,
-                    "share_of_step": {k: v / (ms_total / K) for k, v in kernel_ms.items()}}
+                    "algorithmic": f"F_lqr(n={n},m={m},N={N}) = {f_lqr(n, m, N) / 1e6:.2f} MFLOP per solve x {E} solves per step",
+                    "dominant_kernel": dom, "kernel_ms": kernel_ms,
+                    "share_of_step": {k: v / (ms_total / K) for k, v in kernel_ms.items()},
+                    "lq_kernel": {"kernel": lq_kernel, "achieved": flq / lq_s / 1e12, "frac": flq / lq_s / 1e12 / fp32_peak,
+                                  "unit": "TFLOP/s", "traffic": tr.get("lq_solve_dram_bytes_per_launch"),
+                                  "hbm": {"achieved": blq / lq_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                          "frac": (blq / lq_s / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                          "algorithmic": f"{lq_bytes(n, m, N) / 1e6:.3f} MB per solve (dense LQ data read once + outputs written once)"}}}
         latency = None
         if world == 1 and not args.no_latency:
             latency = latency_leg(dev, ticks=args.latency_ticks)
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, ms = cpu_arm(robot, 1, 0, cores)
+            v, ms, cores = cpu_arm(robot, 2, 1, args.ref_envs)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{cores} solves of the same workload, one per process (float32 torch restatement of the reference)"}
+                            "sample": f"{args.ref_envs} environments of the same workload per batched call, 2 timed calls after 1 warm-up "
+                                      "(float32 torch restatement of the reference, vmap over environments and knots, all host cores)"}
         line = {"metric": METRIC, "value": E * world * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
                 "warmup": max(Wm, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "robot": robot, "envs_per_gpu": E, "n": n, "m": m, "horizon": N,
-                           "lq": lq_name, "limited_memory": lm, "sqp_iterations_per_step": 1,
+                           "lq": lq_name, "limited_memory": lm, "cost_structure": "diagonal W (structured kernels)" if structured else "dense W",
+                           "sqp_iterations_per_step": 1,
                            "l2": "per-step working set (workspace %.0f MB) exceeds the 126 MB L2; no flush" % (solver.ws_bytes / 1e6),
                            "parallelism": f"env-sharded x{world}, no collective on the solve path"},
-                "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "e2e": e2e, "gpu_launches": loop.launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "latency": latency, "clocks": clocks, "nonfinite_envs": nonfinite_envs,
-                "alpha_index_hist_last_step": alpha_hist}
+                "alpha_index_hist_last_step": alpha_hist, "strong": strong}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -536,6 +607,9 @@ def main():
     ap.add_argument("--latency-ticks", type=int, default=1000)
     ap.add_argument("--prewarm-s", type=float, default=2.0, help="seconds of untimed device pre-warm before the warm-up steps")
     ap.add_argument("--ref-max-steps", type=int, default=4)
+    ap.add_argument("--ref-envs", type=int, default=64, help="environments per step of the CPU arm / cpu_baseline")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (Go2 / H1 x4096 over the ranks)")
+    ap.add_argument("--strong-envs", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

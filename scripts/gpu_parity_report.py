@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity  # noqa: E402
-from golden_check import load, solve, LIN, LQ, REL_TOL, TOL_CAP  # noqa: E402
+from golden_check import load, solve, LIN, LQ, REL_TOL, TOL_CAP, tolerance  # noqa: E402
 from mpx_b200 import _lib  # noqa: E402
 
 robots = sys.argv[1].split(",") if len(sys.argv) > 1 else ["srbd", "go2", "aliengo", "h1", "talos"]
@@ -27,7 +27,7 @@ for robot in robots:
             E = g["x0"].shape[0]
             worst = {}
             for e in range(E):
-                tol = lambda key: max(REL_TOL, min(4 * g.budget(key, e), TOL_CAP if key.endswith("_scan") else 1.0))
+                tol = lambda key: tolerance(g, key, e)
                 items = [(nm, solver.view(nm)[e], g[nm][e], nm) for nm in (LIN if mname in ("seq", "seq3") else ())]
                 items += [(nm, solver.view(nm)[e], g[nm + sfx][e], nm + sfx) for nm in LQ]
                 items += [(nm, got[e], g[nm + sfx][e], nm + sfx) for nm, got in (("X", X), ("U", U), ("V", V))]

@@ -14,7 +14,11 @@ reference algorithm on the same inputs:
   summed in the opposite order), un-permuted afterwards;
 * for the associative scan: the suffix products combined right-to-left AND as a balanced (Hillis-Steele) tree --
   lax.associative_scan evaluates a tree, the CUDA kernels evaluate either, the result is the same product in exact
-  arithmetic.
+  arithmetic;
+* the whole float32 oracle (linearisation + LQ solve) on inputs that differ from the fixture's by ONE FLOAT32 ULP of
+  relative noise (three draws): the iterate X (knots >= 1), U, V and the reference trajectory each move by at most
+  2^-23 relative.  Any float32 caller already rounds its inputs this much, so whatever this moves in the
+  outputs is accuracy no float32 implementation can claim (forward error = condition x unit roundoff).
 
 The GPU tests accept  max(1e-4, 4 x budget).
 """
@@ -101,6 +105,25 @@ def budgets_of(robot, case):
                     put(nm + sfx, e, parity.block_rel_err(nm, npy(a[e]), g[nm + sfx][e], segs))
             for nm in ("theta", "phi"):
                 put(nm + sfx, e, rel_arr(npy(det32[nm][e]), g[nm + sfx][e]))
+        # one float32 ulp of input noise, whole pipeline
+        for draw in range(3):
+            rng = np.random.default_rng(1000 + draw)
+            jit = lambda a: np.asarray(a, dtype=np.float64) * (1.0 + 2.0 ** -23 * rng.uniform(-1, 1, np.shape(a)))
+            detp = {}
+            X0p = jit(g["X0"])
+            X0p[:, 0] = g["X0"][:, 0]   # the measured state and knot 0 of the iterate stay as they are (c_0 = x0 - X_0 exactly)
+            bp32.mpc(not scan, jit(g["reference"]), g["parameter"], g["x0"], X0p, jit(g["U0"]), jit(g["V0"]), detail=detp)
+            for e in range(E):
+                if not scan:
+                    for nm in LIN:
+                        put(nm, e, parity.block_rel_err(nm, npy(detp[nm][e]), g[nm][e], segs,
+                                                        magnitude=g["X0"][e] if nm == "c" else None))
+                alpha = 2.0 ** (-int(g["alpha_index" + sfx][e]))
+                for nm in LQ:
+                    put(nm + sfx, e, parity.block_rel_err(nm, npy(detp[nm][e]), g[nm + sfx][e], segs))
+                for nm, base, d in (("X", "X0", "dX"), ("U", "U0", "dU"), ("V", "V0", "dV")):
+                    a = t32(g[base][e]) + alpha * detp[d][e]
+                    put(nm + sfx, e, parity.block_rel_err(nm, npy(a), g[nm + sfx][e], segs))
     return out
 
 

@@ -18,6 +18,15 @@ LIN = ("A", "B", "Q", "R", "M", "q", "r", "c")
 LQ = ("K", "k", "P", "p", "dX", "dU", "dV")
 
 
+def tolerance(g, key, e):
+    """max(1e-4, 4 x FP32 budget); the part of a scan-mode budget that exceeds the sequential budget of the same
+    quantity is capped at TOL_CAP (see above)."""
+    if key.endswith("_scan"):
+        seq = g.budget(key[:-5], e) if key[:-5] in g.budgets else 0.0
+        return max(REL_TOL, min(4 * g.budget(key, e), max(TOL_CAP, 4 * seq)))
+    return max(REL_TOL, 4 * g.budget(key, e))
+
+
 class Fixture:
     """A golden fixture (tests/golden/<robot>_<case>.npz) with its FP32 budgets (tests/golden/budgets_<robot>.json,
     made by tests/golden/make_budgets.py): fx["A"] reads an array, fx.budget("A", e) the budget of environment e."""
@@ -59,7 +68,7 @@ def check_step(cfg, g, solver, X, U, V, sfx, eager):
     E = g["x0"].shape[0]
     fails = []
     for e in range(E):
-        tol = lambda key: max(REL_TOL, min(4 * g.budget(key, e), TOL_CAP if key.endswith("_scan") else 1.0))
+        tol = lambda key: tolerance(g, key, e)
         for nm in LIN:
             err = parity.block_rel_err(nm, solver.view(nm)[e].cpu().numpy(), g[nm][e], segs,
                                        magnitude=g["X0"][e] if nm == "c" else None)
