@@ -329,7 +329,6 @@ class Loop:
 
 def run_native(args):
     import ctypes as C
-    import socket
     import torch
     import torch.distributed as dist
     from mpx_b200 import _lib
@@ -342,13 +341,15 @@ def run_native(args):
         raise RuntimeError("bench.py native arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    nccl_log = None
+    # stdout carries the one JSON line and nothing else: everything any library prints to file descriptor 1 during the
+    # run (NCCL's version banner and its INFO log: communicator ranks, transports, NVLS) is sent to stderr, where the
+    # driver can read it; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries the one JSON line only: NCCL's INFO log goes to one file per rank and is echoed to stderr below
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "mpxb_nccl_%h_%p.log"))
-        nccl_log = os.environ["NCCL_DEBUG_FILE"].replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     robot, desc = WORKLOADS[args.workload]
     E, K, Wm = args.envs, args.steps, args.warmup
@@ -513,14 +514,6 @@ def run_native(args):
             del lp
             torch.cuda.empty_cache()
 
-    if nccl_log and os.path.exists(nccl_log):
-        # the communicator's own account of itself (ranks, transports, NVLS), for whoever reads the run's stderr
-        keep = ("nranks", "Init COMPLETE", "NVLS", "Connected all", "comm 0x")
-        for ln in open(nccl_log, errors="replace"):
-            if any(k in ln for k in keep):
-                sys.stderr.write(ln)
-        sys.stderr.flush()
-
     if rank == 0:
         peaks = {}
         try:
@@ -585,7 +578,8 @@ def run_native(args):
                 "e2e": e2e, "gpu_launches": loop.launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "latency": latency, "clocks": clocks, "nonfinite_envs": nonfinite_envs,
                 "alpha_index_hist_last_step": alpha_hist, "strong": strong}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
