@@ -803,12 +803,44 @@ template <int K> HD void wb_tri_solve(const float* Lm, int ld, const float* idL,
   }
 }
 
+#ifdef __CUDACC__
+// Cholesky of a K x K SPD matrix (K <= 32, lower triangle of Mat valid) by ONE warp with the rows in registers: lane i
+// keeps row i, the update is right-looking with one shuffle per (column, row) pair, no barrier and no shared-memory
+// traffic inside.  Every entry sees the same operations in the same order as the shared-memory column form
+// (s = M_ik - sum_j L_ij L_kj, j ascending, fmaf(-a, b, s); L_ij = s / sqrt(pivot)), so the factor is bitwise the same.
+// Writes the strictly-lower factor back into Mat and the reciprocal diagonal into dinv.
+template <int K, int LD>
+__device__ __forceinline__ void wb_warp_cholesky(float* Mat, float* dinv, int lane) {
+  static_assert(K <= 32, "one row per lane");
+  float row[K];
+  const int r = lane < K ? lane : K - 1;  // spare lanes mirror the last row; their results are discarded
+#pragma unroll
+  for (int c = 0; c < K; ++c) row[c] = (c <= r) ? Mat[r * LD + c] : 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float sjj = __shfl_sync(0xffffffffu, row[j], j);
+    const float dj = 1.f / sqrtf(sjj);
+    const float lij = row[j] * dj;
+    if (lane == j) dinv[j] = dj;
+    if (lane > j && lane < K) Mat[lane * LD + j] = lij;
+#pragma unroll
+    for (int c = j + 1; c < K; ++c) {
+      const float lcj = __shfl_sync(0xffffffffu, lij, c);
+      row[c] = fmaf(-lij, lcj, row[c]);
+    }
+  }
+}
+#endif
+
 // Per-knot primal workspace of the analytic contact solve (shared memory in the kernel)
 template <int NV, int NC> struct WbKnot {
   static constexpr int NF = 3 * NC, NX = 13 + 2 * (NV - 6) + 2 * NF;
   float M[NV * NV];      // qM -> strictly-lower Cholesky factor in place (diagonal in dL)
   float J[NV * NF], MiJ[NV * NF], JMJ[NF * NF];
-  float dL[NV], dLc[NF], D[NV]  /* dL, dLc: reciprocal Cholesky diagonals */, tmd[NV], w[NV], a[NV], z[NV], wvz[NV];
+  // dL, dLc: reciprocal Cholesky diagonals.  tmd sits in front of the read-only D on purpose: the compiler reads tmd with
+  // 16-byte loads that run two floats past its end, and with w behind it racecheck flags that (unused) over-read against
+  // the workers writing w in the same phase.
+  float dL[NV], dLc[NF], tmd[NV], D[NV], w[NV], a[NV], z[NV], wvz[NV];
   float y[NF], grf[NF], feet[NF];
   float xn[NX], Gq[16], Gw[12];
   // explicit-inverse variant (quadruped kernels only, NV <= 18): L^-1 and the right-hand side of the GRF solve
@@ -822,12 +854,18 @@ template <int NV, int NC, bool TANGENT = true, class Sync>
 HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u, const float* contact, int lane,
                      int nl, Sync sync) {
   constexpr int NF = 3 * NC;
-  const int nv = md.nv, nj = md.nj, nf = 3 * md.nc;
+  constexpr int nv = NV, nj = NV - 6, nf = NF;  // every robot class is instantiated for its exact sizes (wb_launch.h)
   const float* qvel = x + 7 + nj;
   for (int i = lane; i < nv; i += nl) k.tmd[i] = (i < 6 ? 0.f : u[i - 6]) - k.D[i];
   for (int idx = lane; idx < nv * NF; idx += nl) k.MiJ[idx] = k.J[idx];
   sync();
   // Cholesky of qM, one column per step; every worker recomputes the pivot so a single barrier per column suffices
+#ifdef __CUDA_ARCH__
+  if (nl >= 32) {  // device: warp 0 factors with the rows in registers (wb_warp_cholesky), the other warps wait
+    if (lane < 32) wb_warp_cholesky<NV, NV>(k.M, k.dL, lane);
+    sync();
+  } else
+#endif
   for (int j = 0; j < nv; ++j) {
     float sjj = k.M[j * NV + j];
     for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
@@ -876,6 +914,14 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
       }
     }
     sync();
+#ifdef __CUDA_ARCH__
+    if (nl >= 32 && NF <= 32) {
+      if constexpr (NF <= 32) {
+        if (lane < 32) wb_warp_cholesky<NF, NF>(k.JMJ, k.dLc, lane);
+      }
+      sync();
+    } else
+#endif
     for (int j = 0; j < nf; ++j) {
       float sjj = k.JMJ[j * NF + j];
       for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
@@ -965,11 +1011,17 @@ template <int NV, int NC, bool TANGENT = true, class Sync>
 HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u, const float* contact,
                          int lane, int nl, Sync sync) {
   constexpr int NF = 3 * NC;
-  const int nv = md.nv, nj = md.nj, nf = 3 * md.nc;
+  constexpr int nv = NV, nj = NV - 6, nf = NF;  // every robot class is instantiated for its exact sizes (wb_launch.h)
   const float* qvel = x + 7 + nj;
   for (int i = lane; i < nv; i += nl) k.tmd[i] = (i < 6 ? 0.f : u[i - 6]) - k.D[i];
   sync();
   // Cholesky of qM, one column per step; every worker recomputes the pivot so a single barrier per column suffices
+#ifdef __CUDA_ARCH__
+  if (nl >= 32) {  // device: warp 0 factors with the rows in registers (wb_warp_cholesky), the other warps wait
+    if (lane < 32) wb_warp_cholesky<NV, NV>(k.M, k.dL, lane);
+    sync();
+  } else
+#endif
   for (int j = 0; j < nv; ++j) {
     float sjj = k.M[j * NV + j];
     for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
@@ -1032,6 +1084,14 @@ HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, c
       }
     }
     sync();
+#ifdef __CUDA_ARCH__
+    if (nl >= 32 && NF <= 32) {
+      if constexpr (NF <= 32) {
+        if (lane < 32) wb_warp_cholesky<NF, NF>(k.JMJ, k.dLc, lane);
+      }
+      sync();
+    } else
+#endif
     for (int j = 0; j < nf; ++j) {
       float sjj = k.JMJ[j * NF + j];
       for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);

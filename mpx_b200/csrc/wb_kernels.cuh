@@ -580,19 +580,42 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
   }
   __syncthreads();
-  wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
-  __syncthreads();
+  // structured mode: the narrow tree stages S1-S4 (4 to ~20 work items) run on warp 0 alone, with warp-level barriers,
+  // while the other warps do the cost preparation and the Gauss-Newton diagonals, which need x, u and the reference only
+  const bool overlap = o.compact && !term;
+  if (!overlap) {
+    wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
+    __syncthreads();
+  }
 
   if (!term) {
     auto sync = [] { __syncthreads(); };
-    wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, NT);
-    __syncthreads();
-    wb_tree_bodies(md, sm.tr, sx, sm.k.feet, tid, NT);
-    __syncthreads();
-    wb_tree_composite(md, sm.tr, tid, NT);
-    __syncthreads();
-    wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
-    __syncthreads();
+    if (overlap) {
+      if (tid < 32) {
+        wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, 32);
+        __syncwarp();
+        wb_tree_bodies(md, sm.tr, sx, sm.k.feet, tid, 32);
+        __syncwarp();
+        wb_tree_composite(md, sm.tr, tid, 32);
+        __syncwarp();
+        wb_tree_dofs(md, sm.tr, sm.k.D, tid, 32);
+      } else {
+        wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid - 32, NT - 32);
+        if constexpr (NT == 64) __syncwarp();
+        else asm volatile("bar.sync 1, %0;" ::"n"(NT - 32) : "memory");
+        wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid - 32, NT - 32);
+      }
+      __syncthreads();
+    } else {
+      wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, NT);
+      __syncthreads();
+      wb_tree_bodies(md, sm.tr, sx, sm.k.feet, tid, NT);
+      __syncthreads();
+      wb_tree_composite(md, sm.tr, tid, NT);
+      __syncthreads();
+      wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
+      __syncthreads();
+    }
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
     // explicit qM^-1 pays for the 18-dof quadrupeds (no spills, shorter chains); measured slower for H1 / Talos
@@ -657,7 +680,7 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     }
   if (o.compact) {
     // diagonal W: no staging, the Gauss-Newton blocks are a few hundred numbers
-    wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
+    if (!overlap) wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
     wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, nullptr);
     return;
   }

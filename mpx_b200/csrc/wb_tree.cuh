@@ -47,7 +47,7 @@ template <class A, class B> HD float dot6(const A* a, const B* b) {
 template <int NB, int NV, int NC, int NI>
 HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* qpos, const float* qvel, int lane, int nl) {
   for (int lf = lane; lf < md.nleaf; lf += nl) {
-    float pos[3], quat[4], cv[6], ca[6];
+    float pos[3], quat[4], cv[6], ca[6], vt0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float ref[3] = {qpos[0], qpos[1], qpos[2]};
     const int len = md.leaf_len[lf];
     for (int lvl = 0; lvl < len; ++lvl) {
@@ -59,7 +59,7 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
         normalize_with_norm<float, 4>(qpos + 3, quat);
         quat_to_mat(quat, Rb);
         for (int i = 0; i < 3; ++i) { cv[i] = 0.f; cv[3 + i] = qvel[i]; ca[i] = 0.f; ca[3 + i] = -md.gravity[i]; }
-        for (int i = 0; i < 6; ++i) { tr.vt[i] = cv[i]; tr.cg[i] = ca[i]; }
+        for (int i = 0; i < 6; ++i) { tr.vt[i] = cv[i]; tr.cg[i] = ca[i]; vt0[i] = cv[i]; }
         float cd[3][6];
         for (int a = 0; a < 3; ++a) {
           const float cdr[6] = {Rb[a], Rb[3 + a], Rb[6 + a], 0.f, 0.f, 0.f};
@@ -123,7 +123,7 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
       if (lvl == 0)
         for (int k = 0; k < 6; ++k) {
           for (int a = 0; a < 3; ++a) tr.rv[a][k] = 0.f;
-          for (int a = 3; a < 6; ++a) tr.rv[a][k] = cv[k] + tr.vt[k];
+          for (int a = 3; a < 6; ++a) tr.rv[a][k] = cv[k] + vt0[k];  // own copy: the other leaf workers write tr.vt too
         }
     }
   }
@@ -133,7 +133,7 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
 template <int NB, int NV, int NC, int NI>
 HD void wb_tree_bodies(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* qpos, float* feet, int lane, int nl) {
   const int nb = md.nbody;
-  for (int b = 1 + lane; b < nb + md.nc; b += nl) {
+  for (int b = 1 + lane; b < nb + NC; b += nl) {
     if (b >= nb) {
       const int c = b - nb, bc = md.contact_body[c];
       float r[3];
@@ -186,7 +186,7 @@ HD void wb_tree_composite(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, int lan
 // ---- stage 4: U_i, qfrc_bias, qM (full symmetric), foot Jacobians
 template <int NB, int NV, int NC, int NI>
 HD void wb_tree_dofs(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, float* D, int lane, int nl) {
-  for (int i = lane; i < md.nv; i += nl) {
+  for (int i = lane; i < NV; i += nl) {
     const int b = md.dof_body[i];
     float f[6];
     inert_mul(tr.Ic[b], tr.S[i], f);
@@ -197,7 +197,7 @@ HD void wb_tree_dofs(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, float* D, in
 template <int NB, int NV, int NC, int NI>
 HD void wb_tree_mass_jac(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, float* M, float* J, int lane, int nl) {
   constexpr int NF = 3 * NC;
-  const int nv = md.nv;
+  constexpr int nv = NV;  // classes are instantiated for their exact sizes (wb_launch.h)
   for (int idx = lane; idx < NV * NV; idx += nl) {
     const int i = idx / NV, j = idx - i * NV;
     float s = 0.f;
@@ -211,7 +211,7 @@ HD void wb_tree_mass_jac(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, fl
   for (int idx = lane; idx < NV * NC; idx += nl) {
     const int i = idx / NC, c = idx - i * NC;
     float jc[3] = {0.f, 0.f, 0.f};
-    if (i < nv && c < md.nc && ((md.contact_dofmask[c] >> i) & 1u)) {
+    if (i < nv && c < NC && ((md.contact_dofmask[c] >> i) & 1u)) {
       float cr[3];
       cross3(tr.S[i], tr.rc[c], cr);
       for (int k = 0; k < 3; ++k) jc[k] = tr.S[i][3 + k] + cr[k];
@@ -269,7 +269,7 @@ HD void wb_dir_frame(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, int D,
 // ---- stage 6: per (direction, body-in-subtree) force perturbations g' / g'', then subtree sums inside each direction
 template <int NB, int NV, int NC, int NI, class Sync>
 HD void wb_tree_items(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, int lane, int nl, Sync sync) {
-  const int npos = 4 + md.nj;
+  constexpr int npos = 4 + NV - 6;
   for (int it = lane; it < md.nitems; it += nl) {
     const int D = md.item_dir[it];
     const int b = md.dir_b0[D] + it - md.dir_off[D];
@@ -301,7 +301,7 @@ HD void wb_tree_items(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, int lane, i
     for (int k = 0; k < 6; ++k) tr.g[it][k] = t[k] + t2[k] + t3[k];
   }
   sync();
-  const int ndir = npos + md.nv;
+  constexpr int ndir = npos + NV;
   for (int idx = lane; idx < ndir * 6; idx += nl) {
     const int D = idx / 6, k = idx - D * 6;
     const int b0 = md.dir_b0[D], off = md.dir_off[D];
@@ -327,7 +327,7 @@ HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const 
       for (int i = 0; i < 3; ++i) dfeet[3 * c + i] = (i == col) ? 1.f : 0.f;
     return;
   }
-  const int D = col - 3, npos = 4 + md.nj;
+  const int D = col - 3, npos = 4 + NV - 6;
   const int b0 = md.dir_b0[D], nbd = md.dir_nb[D], off = md.dir_off[D];
   if (D >= npos) {
     const int dof = D - npos;
@@ -388,7 +388,7 @@ HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const 
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int bc = md.contact_body[c];
-    if (c >= md.nc || bc < b0 || bc >= b0 + nbd) continue;
+    if (bc < b0 || bc >= b0 + nbd) continue;
     float p[3], hc[3] = {0.f, 0.f, 0.f};
     cross3(Sd, tr.rc[c], p);
 #pragma unroll
@@ -428,7 +428,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
                           const float* a, const float* z, const float* y, const float* grf, const float* wvz,
                           WbDirW<NV>* dw, float* fold, int FW, int lane, int nl, Sync sync) {
   constexpr int NF = 3 * NC, NQ = NV + 1;
-  const int npos = 4 + md.nj, ncol = NQ + md.nv;
+  constexpr int npos = 4 + NV - 6, ncol = NQ + NV;
   // F1
   for (int col = 3 + lane; col < NQ; col += nl) {
     const int D = col - 3;
@@ -453,7 +453,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
       for (int k = 0; k < 6; ++k) { d.mu[kk][k] = mu[k]; d.X[1 + kk][k] = Xk[k] + t[k]; }
     }
     uint32_t moves = 0;
-    for (int i = 0; i < md.nv; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int bi = md.dof_body[i];
       if (isq ? (i >= 3) : (bi >= b0 && bi < b0 + nbd)) moves |= 1u << i;
     }
@@ -475,7 +475,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
         if (bi >= b0 && bi < b0 + nbd) s = dot6(tr.S[i], tr.g[off + bi - b0]);
         else if ((md.dof_anc[D - npos] >> i) & 1u) s = dot6(tr.S[i], tr.g[off]);
         t1 = -s; t2 = -s;
-      } else if (col >= 3 && i < md.nv) {
+      } else if (col >= 3) {
         const WbDirW<NV>& d = dw[col];
         const bool mv = (d.moves >> i) & 1u;
         if (mv) {
@@ -489,7 +489,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
           t2 = -(dD + dot6(tr.S[i], d.X[2]));
           e = -dot6(tr.S[i], d.X[3]);
         }
-        for (int c = 0; c < md.nc; ++c) {  // foot Jacobian terms of this dof, feet in fixed order
+        for (int c = 0; c < NC; ++c) {  // foot Jacobian terms of this dof, feet in fixed order
           const int bc = md.contact_body[c];
           if (bc < d.b0 || bc >= d.b0 + d.nbd || !((md.contact_dofmask[c] >> i) & 1u)) continue;
           float dJ[3];
@@ -516,7 +516,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
       float hc[3] = {0.f, 0.f, 0.f}, df[3] = {0.f, 0.f, 0.f};
       if (col < 3) {
         df[col] = 1.f;
-      } else if (col < NQ && c < md.nc) {
+      } else if (col < NQ) {
         const WbDirW<NV>& d = dw[col];
         const int bc = md.contact_body[c];
         if (bc >= d.b0 && bc < d.b0 + d.nbd) {
@@ -524,7 +524,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
           cross3(d.Sd, tr.rc[c], pc);
           for (int k = 0; k < 3; ++k) { pc[k] += d.Sd[3 + k]; df[k] = pc[k]; }
           const uint32_t mask = md.contact_dofmask[c];
-          for (int i = 0; i < md.nv; ++i) {
+          for (int i = 0; i < NV; ++i) {
             if (!((mask >> i) & 1u)) continue;
             float dJ[3];
             if ((d.moves >> i) & 1u) cross3(d.Sd, J + i * NF + 3 * c, dJ);
