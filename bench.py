@@ -301,7 +301,7 @@ class Loop:
             for _ in range(n_warm + K):
                 wrap.run(x0, T(st["cmd"]), feet, torch.ones(E, nc, device=dev))
                 tape.append((wrap.reference, wrap.parameter, x0))
-                x0 = wrap.X[:, shift, :].clone()
+                x0 = self._advance(x0, wrap.X[:, shift, :])
                 feet = wrap.parameter[:, 0, 4:].clone()
             self.x_init = tape[0][2]
             X0 = wrap.initial_state.repeat(E, N + 1, 1).contiguous()
@@ -311,7 +311,7 @@ class Loop:
             for _ in range(n_warm + K):
                 d, _ = wrap.run(d, x0, cmd)
                 tape.append((wrap.reference, wrap.parameter, x0))
-                x0 = wrap.X[:, shift, :].clone()
+                x0 = self._advance(x0, wrap.X[:, shift, :])
             self.x_init = tape[0][2]
             X0 = self.x_init[:, None, :].repeat(1, N + 1, 1).contiguous()
         self.tape, self.pos = tape, 0
@@ -319,6 +319,16 @@ class Loop:
         self.V0 = torch.zeros(E, N + 1, n, device=dev)
         self.X, self.U, self.V = torch.empty_like(self.X0), torch.empty_like(self.U0), torch.empty_like(self.V0)
         self.launches_per_step = self.solver.launches_per_call + 1
+
+    @staticmethod
+    def _advance(x0, x_next):
+        """Closed loop on the model: x0 <- X[shift].  An environment whose solve came back non-finite (FP32 loses the
+        positive definiteness of R + B'PB on a badly conditioned iterate -- the float32 oracle fails on the same inputs,
+        scripts/check_nonfinite_oracle.py; the reference reports it in-band as NaN and its wrapper falls back to the
+        initial guess, mpc_wrapper.py:96) keeps its previous state, as a robot whose controller skipped a tick would."""
+        import torch
+        ok = torch.isfinite(x_next).all(1, keepdim=True)
+        return torch.where(ok, x_next, x0).clone()
 
     def step(self):
         reference, parameter, x0c = self.tape[self.pos]

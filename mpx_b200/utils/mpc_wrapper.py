@@ -105,9 +105,20 @@ class BatchedMPCControllerWrapper(_Base):
     def __init__(self, config, n_env, limited_memory=False, device=None):
         """reference mpc_wrapper.py:30-100."""
         self._setup(config, n_env, limited_memory, device)
-        self.reference_generator = partial(
-            mpc_utils.reference_generator, config.use_terrain_estimation, config.N, config.dt, config.n_joints,
-            config.n_contact, self.robot_mass, foot0=config.p_legs0, q0=config.q0, clearence_speed=0.2)
+
+    def reference_generator(self, *, duty_factor, step_freq, step_height, t_timer, x, foot, input, liftoff, contact=None):
+        """The reference's ``self.reference_generator`` (mpc_wrapper.py:76-78: mpc_utils.reference_generator with
+        use_terrain_estimation, N, dt, n_joints, n_contact, robot_mass, foot0, q0 and clearence_speed = 0.2 bound) for
+        every environment, on the device (mpxb_reference_generator).  Keyword arguments as at the call site
+        mpc_wrapper.py:137-147; returns (reference, parameter, liftoff) and leaves its arguments untouched."""
+        x, foot = self._as(x).contiguous(), self._as(foot).contiguous()
+        gait = self._gait(duty_factor, step_freq, step_height, 0.2, False)
+        timer_in = self._as(t_timer).contiguous()
+        liftoff = self._as(liftoff).clone()
+        reference, parameter = self._solver.reference_generator(
+            gait, x, foot, foot.shape[1], self._as(input).contiguous(), None if contact is None else self._as(contact).contiguous(),
+            timer_in, torch.empty_like(timer_in), liftoff)
+        return reference, parameter, liftoff
 
     def make_data(self):
         """reference mpc_wrapper.py:101-114, batched over n_env."""
@@ -168,10 +179,6 @@ class MPCControllerWrapper(_Base):
         """reference mpc_wrapper.py:195-300 (single instance, stateful; numpy in / numpy out)."""
         self._setup(config, 1, limited_memory, device)
         self.foot0 = np.array(config.p_legs0, dtype=np.float64)
-        self._ref_gen = partial(
-            mpc_utils.reference_generator, config.use_terrain_estimation, config.N, config.dt, config.n_joints,
-            config.n_contact, self.robot_mass, foot0=config.p_legs0, q0=config.q0)
-        self._timer_run = mpc_utils.timer_run
         self._solve = self._solver.solve
         self.U0 = self.u_ref.repeat(1, config.N, 1).contiguous()
         self.X0 = self.initial_state.repeat(1, config.N + 1, 1).contiguous()
@@ -235,21 +242,54 @@ class MPCControllerWrapper(_Base):
         print("MPC Controller Reset")
         return
 
-    def runOffline(self, qpos, qvel, reference=None, parameter=None, max_iter=100):
-        """reference mpc_wrapper.py:387-468 with the host `while` loop moved onto the device: one
-        mpxb_mpc_step(max_iter) call runs up to `max_iter` SQP iterations and stops per the reference's rule
-        (last_cost - g*g < 1e-3 and sum(c*c) < 1e-5).  ``reference``/``parameter`` default to ``config.reference(...)``
-        like the reference.  Returns (X, U, reference, iterations)."""
+    def runOffline(self, qpos, qvel, reference=None, parameter=None, max_iter=100, keep_iterates=True):
+        """reference mpc_wrapper.py:387-468: solve the whole horizon offline from ``config.reference`` (the barrel roll,
+        config_barrel_roll.py:91).  The SQP loop runs `mpc` until ``last_cost - g*g < 1e-3 and sum(c*c) < 1e-5`` (g, c at
+        the NEW iterate) or until ``i > max_iter``, i.e. at most ``max_iter + 1`` iterations.
+
+        keep_iterates=True (the reference's behaviour): a host loop like the reference's, one `mpxb_mpc_step` per
+        iteration and one small read-back of the accepted trial point's (g, sum c^2) -- which the line search has
+        already evaluated at the new iterate -- for the stop decision; returns ``(X, U, reference, output)`` with
+        ``output`` = [X0, X_1, X_2, ...] exactly as the reference returns it (examples/barel_roll.py renders them).
+        keep_iterates=False: the same loop on the device (`mpxb_mpc_step` with max_iter + 1 iterations, per-environment
+        done flag, no host round trip); ``output`` is then [X0, X_final] and ``self.offline_iterations`` the count.
+        ``reference`` / ``parameter`` default to ``config.reference(N + 1, dt, n_joints, n_contact, p_legs0, q0)``."""
         cfg = self.config
         x0, _ = self._x0(qpos, qvel)
         if reference is None:
             reference, parameter = cfg.reference(cfg.N + 1, cfg.dt, cfg.n_joints, cfg.n_contact, cfg.p_legs0, cfg.q0)
-        reference = self._as(np.asarray(reference))[None].contiguous()
-        parameter = self._as(np.asarray(parameter))[None].contiguous()
+        reference = self._as(np.asarray(reference, dtype=np.float32))[None].contiguous()
+        # the dynamics read parameter[t, :n_contact] only (models.py:72); the library takes exactly those columns
+        parameter = self._as(np.asarray(parameter, dtype=np.float32)[:, :self._solver.npar])[None].contiguous()
         nq = 13 + cfg.n_joints
-        self.X0[:, :, :nq] = reference[:, :, :nq]
-        solver = optimizers.MpcSolver(cfg, 1, lq_mode=self._solver.lq_mode,
-                                      device=self.device, robot_model=self.model, max_iter=max_iter)
-        X, U, V = solver.solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
-        self.X0, self.U0, self.V0 = X, U, V
-        return X[0], U[0], reference[0], int(solver.iters[0])
+        self.X0 = self.X0.clone()
+        self.X0[:, :, :nq] = reference[:, :, :nq]  # warm start (mpc_wrapper.py:420)
+        output = [self.X0[0].clone()]
+        if not keep_iterates:
+            key = ("offline", int(max_iter))
+            if getattr(self, "_offline_key", None) != key:
+                self._offline_key = key
+                self._offline_solver = optimizers.MpcSolver(cfg, 1, lq_mode=self._solver.lq_mode, device=self.device,
+                                                            robot_model=self.model, max_iter=int(max_iter) + 1)
+            s = self._offline_solver
+            X, U, V = s.solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
+            self.offline_iterations = int(s.iters[0])
+            output.append(X[0].clone())
+        else:
+            s = self._solver
+            last_cost, i = 1e10, 0
+            while True:
+                X, U, V = s.solve(reference, parameter, self.W, x0, self.X0, self.U0, self.V0)
+                self.X0, self.U0, self.V0 = X.clone(), U.clone(), V.clone()
+                output.append(self.X0[0].clone())
+                # (g, sum c^2) of the new iterate = the accepted trial point of this step's line search
+                ai = s.alpha_index[:1].long()
+                gc = torch.stack([s.view("ls_phi")[0, ai[0]], s.view("ls_theta")[0, ai[0]]]).cpu().numpy()
+                l2_cost, viol = float(gc[0]) * float(gc[0]), float(gc[1])
+                i += 1
+                if i > max_iter or (last_cost - l2_cost < 1e-3 and viol < 1e-5) or not np.isfinite(l2_cost):
+                    break
+                last_cost = l2_cost
+            self.offline_iterations = i
+        self.X0, self.U0, self.V0 = X.clone(), U.clone(), V.clone()
+        return self.X0[0], self.U0[0], reference[0], output

@@ -42,11 +42,6 @@ class BatchedMPCControllerWrapper:
         self._solver = optimizers.MpcSolver(config, n_env, device=self.device,
                                             lq_mode=optimizers.wrapper_lq_mode(False, n_env, config.n, config.N))
         self._solve = self._solver.solve
-        self._ref_gen = partial(mpc_utils.reference_generator_srbd, config.use_terrain_estimator, config.N, config.dt,
-                                config.n_contact, mass=config.mass, clearence_speed=config.clearence_speed,
-                                duty_factor=config.duty_factor, step_freq=config.step_freq,
-                                step_height=config.step_height, foot0=config.p_legs0)
-        self._timer_run = mpc_utils.timer_run
         self._gait = _lib.make_gait(config, config.mass, config.duty_factor, config.step_freq, config.step_height,
                                     config.clearence_speed, config.use_terrain_estimator, True)
         self.W = T(config.W)

@@ -183,3 +183,75 @@ def whole_body_interface(m, contact_id, body_id, Kp, Kd, qpos, qvel, grf, foot_r
     tau_mpc = -(J @ grf)[6:]
     mask = torch.repeat_interleave(contact, 3)
     return tau_mpc * mask + (1 - mask) * tau_fb_lin, J
+
+
+def reference_barell_roll(N, dt, n_joints, n_contact, foot0, q0):
+    """mpc_utils.py:316-398, statement by statement (float64 numpy; examples/barel_roll.py:2 enables x64).
+
+    Five phases: full stance (t1), lateral support on FR/RR with a vertical acceleration (t2), flight on the ballistic
+    arc (t3), landing (t4), rest.  The base rolls at 2*3.14/(t2+t3+t4) rad/s through phases 2-4 (quat_integrate knot
+    by knot, :361-377).  The lateral position restarts at zero in every phase and ``3.14`` is the reference's pi --
+    both kept.  Returns (reference [N, 13+nj+7nc], parameter [N, 4nc])."""
+    from . import mjx_math
+    import torch
+    t1, t2, t3, t4 = 0.2, 0.2, 0.3, 0.1
+    z_start, z_land = 0.4, 0.28
+    v_lateral = -0.25 / (t2 + t3)
+    v0 = (z_land - z_start + 0.5 * 9.81 * t3 * t3) / t3
+    roll_speed = 2 * 3.14 / (t2 + t3 + t4)
+    acc = v0 / t2
+    foot0 = np.asarray(foot0, dtype=np.float64).reshape(-1)
+    q0 = np.asarray(q0, dtype=np.float64).reshape(-1)
+    n1, n2, n3, n4 = int(t1 / dt), int(t2 / dt), int(t3 / dt), int(t4 / dt)
+    # :335-341
+    p1 = np.tile(np.array([0, 0, 0.33]), (n1, 1))
+    p1[:, 1] = np.arange(n1) * dt * v_lateral
+    dp1 = np.tile(np.array([0, v_lateral, 0]), (n1, 1))
+    contact1 = np.tile(np.array([1, 1, 1, 1]), (n1, 1))
+    quat1 = np.tile(np.array([1.0, 0, 0, 0]), (n1, 1))
+    omega1 = np.zeros((n1, 3))
+    # :343-349
+    p2 = np.tile(np.array([0, p1[-1, 1], 0.33]), (n2, 1))
+    p2[:, 2] = 0.5 * np.arange(n2) * dt * np.arange(n2) * dt * acc + 0.33
+    p2[:, 1] = np.arange(n2) * dt * v_lateral
+    dp2 = np.tile(np.array([0, v_lateral, 0]), (n2, 1))
+    dp2[:, 2] = np.arange(n2) * dt * acc
+    contact2 = np.tile(np.array([0, 1, 0, 1]), (n2, 1))
+    # :354-367
+    p3 = np.tile(np.array([0, p2[-1, 1], p2[-1, 2]]), (n3, 1))
+    p3[:, 1] = np.arange(n3) * dt * v_lateral
+    dp3 = np.tile(np.array([0, v_lateral, 0]), (n3, 1))
+    for i in range(n3):
+        t = i * dt
+        p3[i, 2] = z_start - 0.5 * 9.81 * t ** 2 + v0 * t
+        dp3[i, 2] = -9.81 * t + v0
+    contact3 = np.zeros((n3, 4))
+    # :369-374
+    p4 = np.tile(np.array([0, p3[-1, 1], z_land]), (n4, 1))
+    dp4 = np.zeros((n4, 3))
+    contact4 = np.ones((n4, 4))
+    # :376-378
+    quat234 = np.tile(np.array([1.0, 0.0, 0, 0]), (n2 + n3 + n4, 1))
+    w = torch.tensor([roll_speed, 0.0, 0.0], dtype=torch.float64)
+    for t in range(1, n2 + n3 + n4):
+        quat234[t] = mjx_math.quat_integrate(torch.as_tensor(quat234[t - 1]), w, dt).numpy()
+    omega234 = np.tile(np.array([roll_speed, 0, 0]), (n2 + n3 + n4, 1))
+    # :380-386
+    n5 = N - (n1 + n2 + n3 + n4)
+    p5 = np.tile(np.array([0, p4[-1, 1], z_land]), (n5, 1))
+    dp5 = np.zeros((n5, 3))
+    quat5 = np.tile(np.array([1.0, 0, 0, 0]), (n5, 1))
+    omega5 = np.zeros((n5, 3))
+    contact5 = np.ones((n5, 4))
+    # :388-398
+    p_ref = np.concatenate([p1, p2, p3, p4, p5])
+    quat_ref = np.concatenate([quat1, quat234, quat5])
+    q_ref = np.tile(q0, (N, 1))
+    dp_ref = np.concatenate([dp1, dp2, dp3, dp4, dp5])
+    omega_ref = np.concatenate([omega1, omega234, omega5])
+    foot_ref = np.tile(foot0, (N, 1)) + np.tile(p_ref, n_contact)
+    foot_ref[:, 2::3] = 0.0
+    contact_sequence = np.concatenate([contact1, contact2, contact3, contact4, contact5])
+    grf_ref = np.zeros((N, 3 * n_contact))
+    return (np.concatenate([p_ref, quat_ref, q_ref, dp_ref, omega_ref, foot_ref, contact_sequence, grf_ref], axis=1),
+            np.concatenate([contact_sequence, foot_ref], axis=1))

@@ -37,12 +37,14 @@ for cub in sorted(os.listdir(td)):
             fresh = True
     break
 print("sass in rep", len(data), "sass in cubin", len(lines))
-outer = collections.defaultdict(lambda: [0, 0, 0])
+outer = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
 for r, ch in zip(data, lines):
     k = ch[-1]
     outer[k][0] += int(r[ix["# Samples"]] or 0)
     outer[k][1] += int(r[ix["Instructions Executed"]] or 0)
     outer[k][2] += int(r[ix["Thread Instructions Executed"]] or 0) if "Thread Instructions Executed" in ix else 0
+    outer[k][3] += 1  # static SASS instructions of the stage (code size: 16 bytes each)
+    outer[k][4] += int(r[ix["stall_no_inst"]] or 0) if "stall_no_inst" in ix else 0
 ts = sum(v[0] for v in outer.values()) or 1
 ti = sum(v[1] for v in outer.values()) or 1
 print("total warp instructions", ti, "samples", ts)
@@ -61,4 +63,4 @@ if os.environ.get("INNER"):
     sys.exit(0)
 for k, v in sorted(outer.items(), key=lambda x: -x[1][0])[:top]:
     lanes = v[2] / v[1] if v[1] else 0
-    print(f"{k[0]}:{k[1]:<5d} samples {100 * v[0] / ts:5.1f}%  inst {100 * v[1] / ti:5.1f}%  lanes/inst {lanes:4.1f}")
+    print(f"{k[0]}:{k[1]:<5d} samples {100 * v[0] / ts:5.1f}%  inst {100 * v[1] / ti:5.1f}%  lanes/inst {lanes:4.1f}  sass {v[3]:6d}  no_inst {100 * v[4] / max(v[0], 1):4.1f}% of its samples")

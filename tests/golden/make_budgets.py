@@ -132,7 +132,7 @@ if __name__ == "__main__":
     for r in robots:
         OUT = os.path.join(HERE, f"budgets_{r}.json")
         table = {}
-        for case in CASES:
+        for case in (("iter",) if r == "barrel_roll" else CASES):
             b = budgets_of(r, case)
             table[f"{r}_{case}"] = {k: [float(f"{x:.4e}") for x in v] for k, v in sorted(b.items())}
             big = {k: f"{max(v):.1e}" for k, v in b.items() if max(v) > 2.5e-5}

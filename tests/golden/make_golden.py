@@ -59,12 +59,28 @@ def pick(alpha64, alpha32, alpha64s, alpha32s, k):
     return sorted(chosen[:k])
 
 
+def barrel_roll_candidates():
+    """Iterates of the offline barrel-roll solve (tests/golden/barrel_roll_offline.npz, made by
+    make_golden_barrel_roll.py; N = 100): the start (accepted step 1/2) and the iterate after 6 SQP iterations (accepted
+    step 1/16).  Two environments keep the fixture at the size of the others."""
+    g = np.load(os.path.join(HERE, "barrel_roll_offline.npz"))
+    its = [(g["X0"], g["U0"], g["V0"]), (g["first_X"][5], g["first_U"][5], g["first_V"][5])]
+    E = len(its)
+    tile = lambda a: np.tile(np.asarray(a, dtype=np.float64)[None], (E,) + (1,) * np.ndim(a))
+    # the dynamics read parameter[t, :4] only (models.py:72); the library takes exactly those columns
+    return {"reference": tile(g["reference"]), "parameter": tile(g["parameter"][:, :4]), "x0": tile(g["x0"]),
+            "X0": np.stack([i[0] for i in its]), "U0": np.stack([i[1] for i in its]), "V0": np.stack([i[2] for i in its])}
+
+
 def make(robot, case):
     cfg = importlib.import_module(f"mpx_b200.config.config_{robot}")
     pr, pr32 = Problem(cfg), Problem(cfg, dtype=torch.float32)
     bp, bp32 = BatchedProblem(pr), BatchedProblem(pr32)
     segs = parity.segments(cfg)
-    inp = synthetic_inputs(pr, E_CAND, seed=SEED, cold_start=(case == "cold"), scale=6.0 if case == "far" else 1.0)
+    if robot == "barrel_roll":
+        inp = barrel_roll_candidates()
+    else:
+        inp = synthetic_inputs(pr, E_CAND, seed=SEED, cold_start=(case == "cold"), scale=6.0 if case == "far" else 1.0)
     if case == "cold" and robot == "talos":
         # Talos at the exact cold start is ill-posed in FP32 in the reference itself: with U = u_ref = 0 the robot is in
         # free fall, the new angular velocity is 0 in exact arithmetic (1e-17 in float64, 2e-8 in float32), and MJX's
@@ -133,5 +149,5 @@ def make(robot, case):
 if __name__ == "__main__":
     robots = sys.argv[1:] or ["srbd", "go2", "aliengo", "h1", "talos"]
     for r in robots:
-        for case in CASE_NAMES:
+        for case in (("iter",) if r == "barrel_roll" else CASE_NAMES):
             make(r, case)

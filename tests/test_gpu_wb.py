@@ -105,3 +105,31 @@ def test_per_env_W_equals_shared():
     torch.cuda.synchronize()
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("structure", ["dense", "diagonal"])
+def test_wb_fp32_breakdown_is_reported_in_band(structure):
+    """An iterate found in the 2048-environment closed loop of bench.py on which FP32 is at the edge of losing the
+    positive definiteness of R + B'PB (tests/golden/go2_illcond.npz; the float32 oracle's Cholesky fails on it, the
+    float64 oracle still solves it -- tests/test_oracle_failure_mode.py).  The reference reports that in-band as NaNs in
+    (X, U, V) (mpc_wrapper.py:96,280).  So does the library: a non-finite solve sets status bit 0 and nothing else --
+    no trap, and the other environments of the batch are untouched.  The structured kernels (what the wrappers bind for
+    the shipped configs) break down on this iterate like the float32 oracle does; the dense kernels, which sum in
+    another order, happen to get through, and must then report a clean status."""
+    import mpx_b200.config.config_go2 as cfg
+    from mpx_b200.primal_dual_ilqr.optimizers import MpcSolver
+    bad = np.load(os.path.join(os.path.dirname(__file__), "golden", "go2_illcond.npz"))
+    good = _load("go2", "warm")
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).contiguous().cuda()
+    keys = ("reference", "parameter", "x0", "X0", "U0", "V0")
+    batch = [T(np.stack([good[k][0], bad[k], good[k][1]])) for k in keys]
+    s = MpcSolver(cfg, 3, limited_memory=True, cost_structure=structure)
+    X, U, V = s.solve(batch[0], batch[1], T(cfg.W), *batch[2:])
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(X[1]).all() and torch.isfinite(U[1]).all() and torch.isfinite(V[1]).all())
+    assert finite == (int(s.status[1]) & 1 == 0)
+    if structure == "diagonal":
+        assert not finite
+    for e, ge in ((0, 0), (2, 1)):
+        assert int(s.status[e]) == 0
+        assert parity.block_rel_err("X", X[e].cpu().numpy(), good["X"][ge], parity.segments(cfg)) < 1e-3
