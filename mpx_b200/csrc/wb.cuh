@@ -832,6 +832,14 @@ __device__ __forceinline__ void wb_warp_cholesky(float* Mat, float* dinv, int la
 }
 #endif
 
+// Robot classes up to this many dofs form qM^-1 explicitly (wb_s3_primal_inv / wb_s3_tangent_inv): the quadrupeds and
+// H1 (no spills at 168 registers; H1 x4096 linearise 21.0 -> 12.7 ms).  Talos (28 dofs, GRFs are controls) keeps the
+// triangular solves: with the explicit inverse two of its scan-mode golden checks move out of tolerance and E = 1 gains
+// nothing (measured, r02).
+#ifndef MPXB_INV_MAXNV
+#define MPXB_INV_MAXNV 25
+#endif
+
 // Per-knot primal workspace of the analytic contact solve (shared memory in the kernel)
 template <int NV, int NC> struct WbKnot {
   static constexpr int NF = 3 * NC, NX = 13 + 2 * (NV - 6) + 2 * NF;
@@ -843,8 +851,8 @@ template <int NV, int NC> struct WbKnot {
   float dL[NV], dLc[NF], tmd[NV], D[NV], w[NV], a[NV], z[NV], wvz[NV];
   float y[NF], grf[NF], feet[NF];
   float xn[NX], Gq[16], Gw[12];
-  // explicit-inverse variant (quadruped kernels only, NV <= 18): L^-1 and the right-hand side of the GRF solve
-  float Li[NV <= 18 ? NV * NV : NV], yr[NF];
+  // explicit-inverse variant (NV <= MPXB_INV_MAXNV): L^-1 and the right-hand side of the GRF solve
+  float Li[NV <= MPXB_INV_MAXNV ? NV * NV : NV], yr[NF];
 };
 
 // Cooperative primal contact solve (models.py:93-115 / 146-167 / 206-215): `lane` of `nl` workers, `sync()` between

@@ -618,8 +618,8 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     }
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
-    // explicit qM^-1 pays for the 18-dof quadrupeds (no spills, shorter chains); measured slower for H1 / Talos
-    if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
+    // explicit qM^-1 for the quadrupeds and H1 (no spills, shorter dependent chains); Talos keeps the triangular solves
+    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
     else wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
     {
       float* c = o.c + (size_t(e) * (N + 1) + t + 1) * n;
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       float* dst = is_u ? B + (tid - NDS) : A + tid;
       const int ld = is_u ? o.ldB : o.ldA;
       auto sink = [&](int i, float v) { dst[i * ld] = v; atv = fmaf(v, svn[i], atv); };
-      if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
+      if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_tangent_inv<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
       else wb_s3_tangent<NV, NC>(md, sm.k, par, is_u, is_u ? tid - NDS : tid, t1, t2, ee, hh, dfeet, sink);
       satv[is_u ? n + tid - NDS : tid] = atv;
     }
@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     __syncthreads();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
-    if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
+    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
     else wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
     for (int i = tid; i < n; i += NT) {
       const float r = sm.k.xn[i] - sm.sxn[i];
@@ -1020,10 +1020,11 @@ inline int wb_class_configure(bool with_interface) {
 
 template <int NB, int NV, int NC>
 inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& io, const TrialOut& to_in, cudaStream_t st) {
-  static const int legacy = [] { const char* v = getenv("MPXB_WB_TRIAL"); return (v && v[0] == '1') ? 1 : 0; }();
-  // the cooperative kernel wins for the quadrupeds at any batch size and for every robot when the batch is too small
-  // to fill the GPU with one warp per trial point (single-instance latency); measured slower for H1 x2048
-  const bool coop_ok = !legacy && h.tree_ok && h.nbody <= NB && (NV <= 18 || io.E * (io.N + 1) <= 148 * 8);
+  static const int legacy = [] { const char* v = getenv("MPXB_WB_TRIAL"); return (v && v[0] == '1') ? 1 : ((v && v[0] == '2') ? 2 : 0); }();
+  // the cooperative kernel wins for the quadrupeds and H1 at any batch size (H1 x4096: 6.0 vs 6.5 ms, r02) and for
+  // every robot when the batch is too small to fill the GPU with one warp per trial point (single-instance latency)
+  // MPXB_WB_TRIAL=1: warp form only; =2: cooperative form for every class and batch size (measurement switches)
+  const bool coop_ok = legacy != 1 && h.tree_ok && h.nbody <= NB && (legacy == 2 || NV <= MPXB_INV_MAXNV || io.E * (io.N + 1) <= 148 * 8);
   TrialOut to = to_in;
   // first pass / eager evaluation: cooperative (if available) resp. warp-per-trial; second pass: both, selected on the
   // device by the number of environments that still need the smaller steps

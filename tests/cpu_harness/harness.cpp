@@ -94,7 +94,7 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   wb_tree_composite(md, tr, 0, 1);
   wb_tree_dofs(md, tr, k.D, 0, 1);
   wb_tree_mass_jac(md, tr, k.M, k.J, 0, 1);
-  if constexpr (NV <= 18) wb_s3_primal_inv<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
+  if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
   else wb_s3_primal<NV, NC>(md, k, x, u, contact, 0, 1, nosync);
   for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
   wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
@@ -112,7 +112,7 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
     const WbStrided t2{fold + NV * FW + cc, FW}, e{fold + 2 * NV * FW + cc, FW}, h{fold + 3 * NV * FW + cc, FW},
         dfeet{fold + (3 * NV + NF) * FW + cc, FW};
     float* cp = col.data();
-    if constexpr (NV <= 18) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
+    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
     else wb_s3_tangent<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
