@@ -6,7 +6,8 @@ from functools import partial
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpxb.so")
+# MPXB_LIB_PATH: another build of the same library (A/B measurements of kernel variants); never a different backend
+LIB_PATH = os.environ.get("MPXB_LIB_PATH") or os.path.join(_HERE, "libmpxb.so")
 
 MAX_BODY, MAX_DOF, MAX_CONTACT = 32, 32, 8
 KIND_SRBD, KIND_QUAD_WB, KIND_H1_WB, KIND_TALOS_WB = 0, 1, 2, 3

@@ -165,10 +165,11 @@ __device__ __forceinline__ void wb_cost_rowsums(const WbModel& md, const ModelIO
   }
 }
 
-template <int NV, int NC>
+template <int NV, int NC, class Sync>
 __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
                                                float* sgrad, const float* satv, const float* sG,
-                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT, const float* Wov = nullptr) {
+                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT, const float* Wov,
+                                               Sync sync) {
   constexpr int NJ = NV - 6, NF = 3 * NC;
   const int N = io.N, n = md.n, m = md.m, nj = NJ, nc = NC, nf = NF;
   const bool term = (t == N);
@@ -207,7 +208,7 @@ __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO&
     cs.y[a] = 0.5f * (s1 + s2);
     cs.part[a] = cs.r[a] * s1;
   }
-  __syncthreads();
+  sync();
   if (tid < 32) {
     float s = 0.f;
     for (int a = tid; a < nw; a += 32) s += cs.part[a];
@@ -234,6 +235,12 @@ __device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO&
       rdst[i] = gi + satv[n + i];
     }
 
+}
+template <int NV, int NC>
+__device__ __forceinline__ void wb_cost_finish(const WbModel& md, const ModelIO& io, const LinOut& o, int e, int t,
+                                               float* sgrad, const float* satv, const float* sG,
+                                               WbCostSmem<NV, NC>& cs, const float* ref, int tid, int NT, const float* Wov = nullptr) {
+  wb_cost_finish<NV, NC>(md, io, o, e, t, sgrad, satv, sG, cs, ref, tid, NT, Wov, [] { __syncthreads(); });
 }
 
 // Gauss-Newton blocks for a DIAGONAL weight matrix W (every shipped config; the host checks it before selecting the
@@ -527,6 +534,12 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 #ifndef MPXB_LIN3_MINB
 #define MPXB_LIN3_MINB (NT <= 64 ? 6 : (NT <= 96 ? 4 : 2))
 #endif
+// knots per CTA: the kernel is ~16 k SASS instructions of straight-line code that every CTA executes once, and
+// instruction fetch is 15 % of its stall samples; KPB > 1 puts KPB knots -- NT threads, one shared-memory struct and one
+// named barrier each, otherwise independent -- into one CTA, so that a fetched line serves KPB x NT / 32 warps
+#ifndef MPXB_LIN3_KPB
+#define MPXB_LIN3_KPB(NT) ((NT) <= 64 ? 2 : 1)
+#endif
 template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
   static constexpr int NW = 12 + 3 * NJ + 2 * NF;
@@ -548,17 +561,26 @@ __device__ __forceinline__ void wb_cp_async16(float* dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
 }
 
-template <int NB, int NV, int NC, int NI, int NT>
-__global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
+template <int NB, int NV, int NC, int NI, int NT, int KPB>
+__global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
+    wb_linearize3_kernel(const WbModel* __restrict__ mdp, ModelIO io, LinOut o) {
   using S = WbLin3Smem<NB, NV, NC, NI, NT>;
   constexpr int NDS = S::NDS, NQ = NV + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  S& sm = *reinterpret_cast<S*>(smem_raw);
+  const int slot = KPB > 1 ? int(threadIdx.x) / NT : 0;
+  const int tid = int(threadIdx.x) - slot * NT;
+  S& sm = reinterpret_cast<S*>(smem_raw)[slot];
   const WbModel& md = *mdp;
-  const int tid = threadIdx.x;
   const int N = io.N;
-  const int e = blockIdx.x / (N + 1), t = blockIdx.x - e * (N + 1);
+  const int item = int(blockIdx.x) * KPB + slot;
+  if (item >= io.E * (N + 1)) return;   // the knots of a CTA share nothing, not even a barrier
+  const int e = item / (N + 1), t = item - e * (N + 1);
   if (io.done && io.done[e]) return;
+  // barrier over the NT workers of this knot
+  auto sync = [slot] {
+    if constexpr (KPB == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(NT) : "memory");
+  };
   const int n = md.n, m = md.m;
   const bool term = (t == N);
   const float* Xt = io.X + (size_t(e) * (N + 1) + t) * n;
@@ -579,17 +601,16 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
     const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
     for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
   }
-  __syncthreads();
+  sync();
   // structured mode: the narrow tree stages S1-S4 (4 to ~20 work items) run on warp 0 alone, with warp-level barriers,
   // while the other warps do the cost preparation and the Gauss-Newton diagonals, which need x, u and the reference only
   const bool overlap = o.compact && !term;
   if (!overlap) {
     wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
-    __syncthreads();
+    sync();
   }
 
   if (!term) {
-    auto sync = [] { __syncthreads(); };
     if (overlap) {
       if (tid < 32) {
         wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, 32);
@@ -602,22 +623,22 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       } else {
         wb_cost_prepare<NV, NC>(md, io, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid - 32, NT - 32);
         if constexpr (NT == 64) __syncwarp();
-        else asm volatile("bar.sync 1, %0;" ::"n"(NT - 32) : "memory");
+        else asm volatile("bar.sync %0, %1;" ::"r"(KPB + 1 + slot), "n"(NT - 32) : "memory");
         wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid - 32, NT - 32);
       }
-      __syncthreads();
+      sync();
     } else {
       wb_tree_fk(md, sm.tr, sx, sx + NQ, tid, NT);
-      __syncthreads();
+      sync();
       wb_tree_bodies(md, sm.tr, sx, sm.k.feet, tid, NT);
-      __syncthreads();
+      sync();
       wb_tree_composite(md, sm.tr, tid, NT);
-      __syncthreads();
+      sync();
       wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
-      __syncthreads();
+      sync();
     }
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
-    __syncthreads();
+    sync();
     // explicit qM^-1 for the quadrupeds and H1 (no spills, shorter dependent chains); Talos keeps the triangular solves
     if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
     else wb_s3_primal<NV, NC>(md, sm.k, sx, su, par, tid, NT, sync);
@@ -632,15 +653,15 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
       }
     }
     wb_tree_acc(md, sm.tr, sm.k.w, sm.k.a, sm.k.z, tid, NT, sync);
-    __syncthreads();
+    sync();
     wb_tree_items(md, sm.tr, tid, NT, sync);
-    __syncthreads();
+    sync();
     float* A = o.A + (size_t(e) * N + t) * n * o.ldA;
     float* B = o.B + (size_t(e) * N + t) * n * o.ldB;
     // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
     // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
     wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync);
-    __syncthreads();
+    sync();
     if (tid < NDS + m) {
       constexpr int FW = S::FW, NF3 = 3 * NC;
       float t1[NV];
@@ -681,25 +702,25 @@ __global__ void __launch_bounds__(NT, MPXB_LIN3_MINB) wb_linearize3_kernel(const
   if (o.compact) {
     // diagonal W: no staging, the Gauss-Newton blocks are a few hundred numbers
     if (!overlap) wb_gn_compact<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT);
-    wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, nullptr);
+    wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, nullptr, sync);
     return;
   }
   // stage W over the dead tree / fold arrays (16-byte cp.async when it is 16-byte aligned and fits)
   const float* Wg = io.W + size_t(e) * io.w_stride;
   const float* Wuse = nullptr;
   const int nww = md.nw * md.nw;
-  __syncthreads();  // every worker is done with tr / fold / dw
+  sync();  // every worker is done with tr / fold / dw
   if ((reinterpret_cast<unsigned long long>(Wg) & 15ull) == 0 && (nww & 3) == 0 &&
       size_t(nww) * sizeof(float) <= sizeof(sm.tr) + sizeof(sm.fold) + sizeof(sm.dw)) {
     float* sW = reinterpret_cast<float*>(&sm.tr);
     for (int v = tid; v < nww / 4; v += NT) wb_cp_async16(sW + 4 * v, Wg + 4 * v);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
+    sync();
     Wuse = sW;
   }
   wb_gn_blocks<NV, NC>(md, io, o, e, t, sx, su, sm.sG, sm.cs, sm.sref, tid, NT, Wuse);
-  wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, Wuse);
+  wb_cost_finish<NV, NC>(md, io, o, e, t, sm.sgrad, satv, sm.sG, sm.cs, sm.sref, tid, NT, Wuse, sync);
 }
 
 // one warp per (env, alpha): lanes stride over knots; deterministic shuffle reduction
@@ -884,8 +905,11 @@ inline int wb_launch_linearize_t(const WbModel& h, const WbModel* dev, const Mod
 template <int NB, int NV, int NC, int NI, int NT>
 inline int wb_launch_linearize3_t(const WbModel& h, const WbModel* dev, const ModelIO& io, const LinOut& lo, cudaStream_t st) {
   using S = WbLin3Smem<NB, NV, NC, NI, NT>;
-  auto kern = wb_linearize3_kernel<NB, NV, NC, NI, NT>;
-  kern<<<io.E * (io.N + 1), NT, sizeof(S), st>>>(dev, io, lo);
+  constexpr int KPB = MPXB_LIN3_KPB(NT);
+  static_assert(sizeof(S) % 16 == 0, "the per-knot structs are laid out back to back");
+  auto kern = wb_linearize3_kernel<NB, NV, NC, NI, NT, KPB>;
+  const int items = io.E * (io.N + 1);
+  kern<<<(items + KPB - 1) / KPB, NT * KPB, KPB * sizeof(S), st>>>(dev, io, lo);
   return cudaGetLastError() == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
@@ -1010,7 +1034,7 @@ template <int NB, int NV, int NC, int MAXD, int NI, int NT>
 inline int wb_class_configure(bool with_interface) {
   auto set = [](auto kern, size_t bytes) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) == cudaSuccess; };
   bool ok = set(wb_linearize_kernel<NV, NC, MAXD, NT>, sizeof(WbLinSmem<NV, NC, MAXD, NT>));
-  ok = ok && set(wb_linearize3_kernel<NB, NV, NC, NI, NT>, sizeof(WbLin3Smem<NB, NV, NC, NI, NT>));
+  ok = ok && set(wb_linearize3_kernel<NB, NV, NC, NI, NT, MPXB_LIN3_KPB(NT)>, MPXB_LIN3_KPB(NT) * sizeof(WbLin3Smem<NB, NV, NC, NI, NT>));
   ok = ok && set(wb_trial3_kernel<NB, NV, NC, 64>, sizeof(WbTrialSmem<NB, NV, NC>));
   if (with_interface) {
     if constexpr (NV == 6 + 3 * NC) ok = ok && set(wb_interface_kernel<NB, NV, NC, 64>, sizeof(WbiSmem<NB, NV, NC>));

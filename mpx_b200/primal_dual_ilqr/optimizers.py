@@ -41,6 +41,20 @@ _LQ_COST_US = {13: (8.9, 15.3, 24.5, 1.2), 61: (18.0, 92.6, 64.0, 2.7), 75: (30.
                81: (79.0, 158.6, 230.0, 4.1)}
 
 
+LQ_MODE_NAMES = {_lib.LQ_SEQUENTIAL: "sequential", _lib.LQ_SCAN: "scan", _lib.LQ_SCAN_SERIAL: "scan_serial",
+                 _lib.LQ_SCAN_PARALLEL: "scan_parallel"}
+
+
+def _sm_count():
+    """SMs of the current CUDA device (one parallel-scan CTA per SM and wave); 148 (B200) when no device is visible."""
+    try:
+        if torch.cuda.is_available():
+            return int(torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
+    except Exception:
+        pass
+    return 148
+
+
 def wrapper_lq_mode(limited_memory, n_env, n, N):
     """Which LQ kernel the controller wrappers bind (an ``_lib.LQ_*`` value).
 
@@ -67,7 +81,7 @@ def wrapper_lq_mode(limited_memory, n_env, n, N):
         return _lib.LQ_SEQUENTIAL
     knot, comb, fixed, roll = _LQ_COST_US[n]
     levels = int(N).bit_length()
-    waves = -(-n_env * (N + 1) // 148)
+    waves = -(-n_env * (N + 1) // _sm_count())
     t_scan = fixed + roll * N + levels * waves * comb
     t_seq = N * knot
     return _lib.LQ_SCAN_PARALLEL if t_scan < t_seq else _lib.LQ_SEQUENTIAL
@@ -93,6 +107,7 @@ class MpcSolver:
                 os.environ.get("MPXB_SCAN_SCHEDULE", "").lower())
             if forced is not None:
                 self.lq_mode = forced
+        self.lq_mode_name = LQ_MODE_NAMES[self.lq_mode]   # which LQ kernel this solver runs (see wrapper_lq_mode)
         self.max_iter = int(max_iter)
         self.desc = _lib.make_desc(config, robot_model)
         self.N, self.n, self.m = self.desc.N, self.desc.n, self.desc.m
@@ -133,14 +148,18 @@ class MpcSolver:
         # kernels per SQP iteration: linearise, LQ, select + the trial kernels (eager: one; lazy: alpha = 1, then the rest;
         # the cooperative whole-body form adds its reduce kernel, and its second pass launches both forms -- see
         # wb_class_trial in csrc/wb_kernels.cuh)
+        wb = self.desc.kind != 0
+        # passes: alpha = 1, [alpha = 1/2 for large H1 / Talos batches,] the rest (mpxb_mpc_step); the cooperative form
+        # (quadrupeds and H1 at any batch size, every robot for small batches) is kernel + reduce in the first pass and
+        # warp form + cooperative form + reduce in the later ones
+        npass = 3 if (wb and self.desc.nv > 18 and self.n_env >= 256) else 2
+        coop = wb and (self.desc.nv <= 25 or self.n_env * (self.N + 1) <= 148 * 8)
         if self.eager_line_search:
             trial = 1
-        elif self.desc.kind != 0 and self.desc.nv > 18 and self.n_env >= 256:
-            trial = 3   # alpha = 1, alpha = 1/2, the rest (warp form; see mpxb_mpc_step)
-        elif self.desc.kind != 0 and (self.desc.nv <= 18 or self.n_env * (self.N + 1) <= 148 * 8):
-            trial = 2 + 3
+        elif coop:
+            trial = 2 + 3 * (npass - 1)
         else:
-            trial = 2
+            trial = npass
         # the parallel-in-time scan is elements + ceil(log2(N+1)) levels + gains + rollout; the other LQ kernels are one launch
         parallel_scan = self.lq_mode == _lib.LQ_SCAN_PARALLEL or (self.lq_mode == _lib.LQ_SCAN and self.n_env <= 64)
         lq = 3 + int(self.N).bit_length() if parallel_scan else 1
@@ -275,7 +294,8 @@ class MpcSolver:
         return tau, q, dq
 
 
-_SOLVERS = {}
+_SOLVERS = {}      # insertion-ordered: least recently used first
+_SOLVERS_MAX = 8
 
 
 def _config_from_partials(cost, dynamics, hessian_approx):
@@ -318,11 +338,17 @@ def mpc(cost, dynamics, hessian_approx, limited_mempory, reference, parameter, W
     E = reference.shape[0]
     key = (id(_unwrap(cost)[0]), _unwrap(cost)[1][-3:], id(_unwrap(dynamics)[0]), id(_unwrap(dynamics)[1][0]),
            bool(limited_mempory), E, reference.device.index)
-    solver = _SOLVERS.get(key)
-    if solver is None:
+    entry = _SOLVERS.pop(key, None)
+    if entry is None:
         cfg, rm = _config_from_partials(cost, dynamics, hessian_approx)
         solver = MpcSolver(cfg, E, bool(limited_mempory), device=reference.device, robot_model=rm)
-        _SOLVERS[key] = solver
+        # the key holds id()s: keep the keyed objects alive beside the solver so that an id cannot be reused for another
+        # model while the entry exists
+        entry = (solver, (_unwrap(cost)[0], _unwrap(dynamics)[0], _unwrap(dynamics)[1][0]))
+    _SOLVERS[key] = entry            # most recently used last
+    while len(_SOLVERS) > _SOLVERS_MAX:
+        _SOLVERS.pop(next(iter(_SOLVERS)))   # evict the least recently used handle + workspace
+    solver = entry[0]
     X, U, V = solver.solve(reference, parameter, W, x0, X_in, U_in, V_in)
     if not batched:
         X, U, V = X[0], U[0], V[0]

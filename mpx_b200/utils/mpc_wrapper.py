@@ -74,6 +74,9 @@ class _Base:
         self._solver = optimizers.MpcSolver(config, n_env, device=self.device,
                                             lq_mode=optimizers.wrapper_lq_mode(limited_memory, n_env, config.n, config.N),
                                             robot_model=self.model, max_iter=max_iter)
+        # limited_memory=False does not mean "associative scan" here: the wrapper binds the fastest LQ kernel for the
+        # shape (optimizers.wrapper_lq_mode); this says which one
+        self.lq_mode_name = self._solver.lq_mode_name
         self.u_ref = self._T(config.u_ref)
         self.W = self._T(config.W)
 

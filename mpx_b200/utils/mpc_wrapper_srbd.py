@@ -42,6 +42,7 @@ class BatchedMPCControllerWrapper:
         self._solver = optimizers.MpcSolver(config, n_env, device=self.device,
                                             lq_mode=optimizers.wrapper_lq_mode(False, n_env, config.n, config.N))
         self._solve = self._solver.solve
+        self.lq_mode_name = self._solver.lq_mode_name   # the LQ kernel bound for this shape (optimizers.wrapper_lq_mode)
         self._gait = _lib.make_gait(config, config.mass, config.duty_factor, config.step_freq, config.step_height,
                                     config.clearence_speed, config.use_terrain_estimator, True)
         self.W = T(config.W)
