@@ -118,7 +118,17 @@ void mpxb_model_destroy(mpxb_model* model);
  * MPXB_OPT_LINE_SEARCH (default MPXB_LS_FILTER): MPXB_LS_FILTER is parallel_filter_line_search, the search the
  * reference's mpc runs (optimizers.py:468-578, 670-681); MPXB_LS_MERIT is parallel_line_search on the augmented
  * Lagrangian merit g + sum((V + rho/2 c) c) with merit_rho / slope (optimizers.py:185-217, 295-354), the call the
- * reference keeps commented out at optimizers.py:637-669.
+ * reference keeps commented out at optimizers.py:637-669.  MPXB_LS_ARMIJO is the sequential backtracking `line_search`
+ * of the legacy solver (old_optimazers.py:173-251; same function at optimizers.py:219-293) with alpha_0 = 1,
+ * alpha_mult = 1/2 and alpha_min = 2^-10, i.e. on the same 11 trial points: the first point that passes the Armijo test
+ * on the merit function with the legacy slope (old_optimazers.py:154-170: sum(dV c) once), else the last point tried
+ * (alpha = 2^-10) with no_errors = false (status bit 1).
+ * MPXB_OPT_STOP_RULE (default MPXB_STOP_OFFLINE), for max_iter > 1: MPXB_STOP_OFFLINE is runOffline's rule
+ * (mpc_wrapper.py:456-467: last_cost - g^2 < 1e-3 and sum c^2 < 1e-5 at the new iterate); MPXB_STOP_LEGACY is the
+ * legacy loop's continuation_criterion (old_optimazers.py:435-447), evaluated on the search direction BEFORE the step
+ * is taken: continue while no_errors and (|merit slope| > 1e-4 and |d|^2 > 0  or  sum c^2 > 1e-4); iters[e] counts
+ * the steps taken.  It needs the merit quantities, so it requires MPXB_LS_MERIT or MPXB_LS_ARMIJO (else MPXB_EINVAL
+ * from mpxb_mpc_step).
  * MPXB_OPT_COST_STRUCTURE (default MPXB_COST_DENSE): MPXB_COST_DIAGONAL_W is the caller's promise that the weight
  * matrix W passed to mpxb_mpc_step is DIAGONAL (every shipped config: block_diag of diag(...), config_*.py).  The
  * Gauss-Newton blocks of the whole-body objectives (objectives.py:127-202, 252-323, 378-450) are then Q_t = diag + a
@@ -127,8 +137,9 @@ void mpxb_model_destroy(mpxb_model* model);
  * multiplied, LQ data in packed blocks moved by bulk asynchronous copies.  X, U, V agree with the dense path to
  * rounding.  The dense views "A".."p" are then filled by mpxb_workspace_expand.  Ignored for MPXB_KIND_SRBD and the
  * scan modes.  A non-diagonal W with this option set gives wrong results (the off-diagonal entries are never read). */
-enum { MPXB_OPT_EAGER_LINE_SEARCH = 1, MPXB_OPT_LINE_SEARCH = 2, MPXB_OPT_COST_STRUCTURE = 3 };
-enum { MPXB_LS_FILTER = 0, MPXB_LS_MERIT = 1 };
+enum { MPXB_OPT_EAGER_LINE_SEARCH = 1, MPXB_OPT_LINE_SEARCH = 2, MPXB_OPT_COST_STRUCTURE = 3, MPXB_OPT_STOP_RULE = 4 };
+enum { MPXB_LS_FILTER = 0, MPXB_LS_MERIT = 1, MPXB_LS_ARMIJO = 2 };
+enum { MPXB_STOP_OFFLINE = 0, MPXB_STOP_LEGACY = 1 };
 enum { MPXB_COST_DENSE = 0, MPXB_COST_DIAGONAL_W = 1 };
 int mpxb_model_set_option(mpxb_model* model, int option, int value);
 
@@ -143,7 +154,7 @@ size_t mpxb_workspace_bytes(const mpxb_model* model, int E, int lq_mode);
  *   reference [E,N+1,nref]  parameter [E,N+1,npar]  W [nw,nw] if w_env_stride == 0 else [E,nw,nw]
  *   x0 [E,n]  X_in/X [E,N+1,n]  U_in/U [E,N,m]  V_in/V [E,N+1,n]
  *   alpha_index [E]  index i of the accepted step 2^-i (10 if none, optimizers.py:572)      (may be NULL)
- *   iters [E], status [E]  (status bit 0: non-finite value in X/U/V)                        (may be NULL)
+ *   iters [E], status [E]  (status bit 0: non-finite value in X/U/V; bit 1: MPXB_LS_ARMIJO ran out of step sizes)                        (may be NULL)
  * X/U/V must not alias X_in/U_in/V_in. */
 int mpxb_mpc_step(const mpxb_model* model, void* stream /* cudaStream_t */, int E, int lq_mode, int max_iter,
                   const float* reference, const float* parameter, const float* W, size_t w_env_stride,

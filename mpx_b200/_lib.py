@@ -14,8 +14,10 @@ KIND_SRBD, KIND_QUAD_WB, KIND_H1_WB, KIND_TALOS_WB = 0, 1, 2, 3
 OPT_EAGER_LINE_SEARCH = 1
 OPT_LINE_SEARCH = 2
 OPT_COST_STRUCTURE = 3
+OPT_STOP_RULE = 4
 COST_DENSE, COST_DIAGONAL_W = 0, 1
-LS_FILTER, LS_MERIT = 0, 1
+LS_FILTER, LS_MERIT, LS_ARMIJO = 0, 1, 2
+STOP_OFFLINE, STOP_LEGACY = 0, 1
 LQ_SEQUENTIAL, LQ_SCAN, LQ_SCAN_SERIAL, LQ_SCAN_PARALLEL = 0, 1, 2, 3
 ERRORS = {0: "ok", -1: "MPXB_EINVAL", -2: "MPXB_EUNSUPPORTED", -3: "MPXB_EWORKSPACE", -4: "MPXB_ECUDA"}
 

@@ -92,11 +92,12 @@ __device__ __forceinline__ bool filter_accept(float theta_new, float phi_new, fl
 
 // Merit line search: rho (merit_rho, optimizers.py:185-198), the current merit g + sum((V + rho/2 c) c) and its slope
 // sum(q dX) + sum(r dU) + 2 sum(dV c) - rho sum(c c) (optimizers.py:201-217)
+// mode: the MPXB_LS_* value (1: optimizers.py:201-217, 2 sum(dV c); 2: the legacy slope old_optimazers.py:154-170, sum(dV c))
 __device__ __forceinline__ void merit_terms(float theta_k, float phi_k, float vc_k, float dv2, float dvc, float slope_lq,
-                                            float* rho, float* merit_k, float* mslope) {
+                                            float* rho, float* merit_k, float* mslope, int mode = 1) {
   *rho = (theta_k > 1e-12f) ? 2.f * sqrtf(dv2 / theta_k) : 1e-2f;
   *merit_k = phi_k + vc_k + 0.5f * *rho * theta_k;
-  *mslope = slope_lq + 2.f * dvc - *rho * theta_k;
+  *mslope = slope_lq + (mode == 2 ? 1.f : 2.f) * dvc - *rho * theta_k;
 }
 // parallel_line_search's step_acceptance (True = the Armijo test FAILS); a NaN merit is replaced by the current one
 __device__ __forceinline__ bool merit_rejected(float theta_new, float phi_new, float vc_new, float rho, float merit_k,
@@ -120,7 +121,7 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
       bool ok;
       if (o.merit) {
         float rho, mk, ms;
-        merit_terms(o.theta_k[e], o.phi_k[e], o.vc_k[e], o.dv2[e], o.dvc[e], o.slope[e], &rho, &mk, &ms);
+        merit_terms(o.theta_k[e], o.phi_k[e], o.vc_k[e], o.dv2[e], o.dvc[e], o.slope[e], &rho, &mk, &ms, o.merit);
         ok = !merit_rejected(theta, phi, vc, rho, mk, ms, exp2f(-float(ia)));
       } else {
         ok = filter_accept(theta, phi, o.theta_k[e], o.phi_k[e], o.slope[e], exp2f(-float(ia)));
@@ -163,7 +164,7 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
     if (o.merit) {
       o.vc_k[e] = vk; o.dv2[e] = d2; o.dvc[e] = dc;
       float rho, mk, ms;
-      merit_terms(th, ph, vk, d2, dc, o.slope[e], &rho, &mk, &ms);
+      merit_terms(th, ph, vk, d2, dc, o.slope[e], &rho, &mk, &ms, o.merit);
       nd = merit_rejected(theta, phi, vc, rho, mk, ms, 1.f) ? 1 : 0;
     } else {
       nd = filter_accept(theta, phi, th, ph, o.slope[e], 1.f) ? 0 : 1;

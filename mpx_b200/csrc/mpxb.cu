@@ -34,7 +34,8 @@ struct mpxb_model {
   SrbdParams srbd;
   WbModel* wb_dev;  // device copy of the whole-body tables (null for SRBD)
   int eager_line_search;  // 1: evaluate all 11 trial points every call (default 0: lazy, same result)
-  int merit_line_search;  // 1: merit-function line search instead of the filter
+  int merit_line_search;  // MPXB_LS_*: 0 filter, 1 parallel merit search, 2 sequential Armijo semantics (legacy slope)
+  int stop_rule;          // MPXB_STOP_*
   int structured;         // MPXB_OPT_COST_STRUCTURE: 1 = W is diagonal (checked by the host) -> structured LQ path
   bool s3_ok;             // the structured kernels are compiled for this model's dimensions
   Lq3Layout s3;
@@ -154,6 +155,7 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   mdl->prof = nullptr;
   mdl->eager_line_search = 0;
   mdl->merit_line_search = 0;
+  mdl->stop_rule = MPXB_STOP_OFFLINE;
   mdl->structured = 0;
   mdl->s3_ok = false;
   if (d->kind != MPXB_KIND_SRBD) {
@@ -202,8 +204,13 @@ int mpxb_model_set_option(mpxb_model* m, int option, int value) {
     return MPXB_OK;
   }
   if (option == MPXB_OPT_LINE_SEARCH) {
-    if (value != MPXB_LS_FILTER && value != MPXB_LS_MERIT) return MPXB_EINVAL;
-    m->merit_line_search = (value == MPXB_LS_MERIT);
+    if (value != MPXB_LS_FILTER && value != MPXB_LS_MERIT && value != MPXB_LS_ARMIJO) return MPXB_EINVAL;
+    m->merit_line_search = value;
+    return MPXB_OK;
+  }
+  if (option == MPXB_OPT_STOP_RULE) {
+    if (value != MPXB_STOP_OFFLINE && value != MPXB_STOP_LEGACY) return MPXB_EINVAL;
+    m->stop_rule = value;
     return MPXB_OK;
   }
   return MPXB_EINVAL;
@@ -255,6 +262,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
   if (!mdl || !reference || !parameter || !W || !x0 || !X_in || !U_in || !V_in || !X || !U || !V || !workspace)
     return MPXB_EINVAL;
   if (E <= 0 || max_iter <= 0) return MPXB_EINVAL;
+  if (mdl->stop_rule == MPXB_STOP_LEGACY && mdl->merit_line_search == MPXB_LS_FILTER) return MPXB_EINVAL;
   if (!lq_mode_valid(lq_mode, E)) return MPXB_EINVAL;
   if (X == X_in || U == U_in || V == V_in) return MPXB_EINVAL;
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return MPXB_EINVAL;  // bulk copies need 16-byte aligned blocks
@@ -345,7 +353,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     SelectArgs sa{E, N, n, m, Xc, Uc, Vc, ws + L.dX, ws + L.dU, ws + L.dV, ws + L.theta_k, ws + L.phi_k, ws + L.ls_theta,
                   ws + L.ls_phi, ws + L.slope, Xn, Un, Vn, ws + L.g, ws + L.last_cost, done, alpha_index, iters,
                   status, max_iter > 1 ? 1 : 0, it == 0 ? 1 : 0, mdl->merit_line_search, ws + L.ls_vc, ws + L.vc_k,
-                  ws + L.dv2, ws + L.dvc};
+                  ws + L.dv2, ws + L.dvc, mdl->stop_rule};
     select_update_kernel<<<E, 128, 0, st>>>(sa);
     if (pev) { cudaEventRecord(pev[4], st); pf->calls++; }
     Xc = Xn; Uc = Un; Vc = Vn;

@@ -85,8 +85,9 @@ struct SelectArgs {
   int32_t *alpha_index, *iters, *status;  // may be null
   int check_convergence;  // 1 when max_iter > 1
   int first_iter;
-  int merit;  // 1: merit-function line search (parallel_line_search), 0: filter
+  int merit;  // MPXB_LS_*: 0 filter, 1 merit-function line search (parallel_line_search), 2 sequential Armijo (legacy)
   const float *ls_vc, *vc_k, *dv2, *dvc;
+  int stop_rule;  // MPXB_STOP_*: 0 runOffline's rule after the step, 1 the legacy continuation criterion before it
 };
 
 // One CTA per env: theta_k, phi_k, filter tests for the 11 trial points, chosen alpha, iterate update.
@@ -105,8 +106,22 @@ __global__ void select_update_kernel(SelectArgs a) {
     for (size_t i = tid; i < nu; i += blockDim.x) Uo[i] = Ui[i];
     return;
   }
-  __shared__ int s_idx;
-  __shared__ float s_alpha;
+  __shared__ int s_idx, s_stop;
+  __shared__ float s_alpha, s_part[32];
+  const bool legacy = a.stop_rule == 1 && a.check_convergence && a.done;
+  float d2 = 0.f;
+  if (legacy) {
+    // |d|^2 = sum dX^2 + sum dU^2 (+ sum dV^2, which the trial kernel has reduced) for the continuation criterion
+    const float* dXe = a.dX + e * nx;
+    const float* dUe = a.dU + e * nu;
+    for (size_t i = tid; i < nx; i += blockDim.x) d2 = fmaf(dXe[i], dXe[i], d2);
+    for (size_t i = tid; i < nu; i += blockDim.x) d2 = fmaf(dUe[i], dUe[i], d2);
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, k);
+    if ((tid & 31) == 0) s_part[tid >> 5] = d2;
+  }
+  if (tid == 0) s_stop = 0;
+  __syncthreads();
   if (tid == 0) {
     // theta_k = sum c^2, phi_k = sum_t cost_t of the current iterate (reduced by the trial kernel)
     const float theta_k = a.theta_k[e], phi_k = a.phi_k[e];
@@ -114,16 +129,34 @@ __global__ void select_update_kernel(SelectArgs a) {
     // first accepted trial point (largest alpha), else index -1 of the 11 trials (optimizers.py:568-572).  Ascending
     // with early exit: when the line search ran lazily the entries behind the first accepted one were never evaluated.
     int best = NALPHA - 1;
+    bool exhausted = false;
     if (a.merit) {
       // parallel_line_search (optimizers.py:295-354): first trial point that passes the Armijo test on the merit
-      // function; index 0 when none does (argmin of an all-True acceptance vector)
+      // function; index 0 when none does (argmin of an all-True acceptance vector).  MPXB_LS_ARMIJO: the sequential
+      // line_search (old_optimazers.py:173-251) on the same points -- none accepted = the last point, no_errors false
       float rho, mk, ms;
-      merit_terms(theta_k, phi_k, a.vc_k[e], a.dv2[e], a.dvc[e], slope, &rho, &mk, &ms);
-      best = 0;
-      for (int i = 0; i < NALPHA; ++i) {
+      merit_terms(theta_k, phi_k, a.vc_k[e], a.dv2[e], a.dvc[e], slope, &rho, &mk, &ms, a.merit);
+      if (legacy) {
+        // continuation_criterion (old_optimazers.py:435-447) on the direction just computed, before the step
+        float dd = a.dv2[e];
+        for (int w = 0; w < int(blockDim.x >> 5); ++w) dd += s_part[w];
+        const bool slope_ok = fabsf(ms) > 1e-4f, delta_ok = dd > 0.f, c_ok = theta_k > 1e-4f;
+        if (!((slope_ok && delta_ok) || c_ok)) {
+          s_stop = 1;
+          a.done[e] = 1;
+          if (a.g_out) a.g_out[e] = phi_k;
+          if (a.iters && a.first_iter) a.iters[e] = 0;
+          if (a.status && a.first_iter) a.status[e] = 0;
+        }
+      }
+      best = (a.merit == 2) ? NALPHA - 1 : 0;
+      exhausted = (a.merit == 2);
+      for (int i = 0; i < NALPHA && !s_stop; ++i) {
         if (!merit_rejected(a.ls_theta[e * NALPHA + i], a.ls_phi[e * NALPHA + i], a.ls_vc[e * NALPHA + i], rho, mk, ms,
                             exp2f(-float(i)))) {
           best = i;
+          // alpha_min = 2^-10: a step accepted AT alpha_min still ends the loop (no_errors = alpha > alpha_min)
+          exhausted = (a.merit == 2) && (i == NALPHA - 1);
           break;
         }
       }
@@ -135,12 +168,15 @@ __global__ void select_update_kernel(SelectArgs a) {
         }
       }
     }
-    s_idx = best;
+    s_idx = exhausted ? -(best + 1) : best;   // negative: MPXB_LS_ARMIJO ran out of step sizes (status bit 1)
     s_alpha = exp2f(-float(best));
-    if (a.g_out) a.g_out[e] = phi_k;
-    if (a.alpha_index) a.alpha_index[e] = best;
-    if (a.iters) a.iters[e] = (a.first_iter ? 0 : a.iters[e]) + 1;
-    if (a.check_convergence && a.done) {
+    if (!s_stop) {
+      if (a.g_out) a.g_out[e] = phi_k;
+      if (a.alpha_index) a.alpha_index[e] = best;
+      if (a.iters) a.iters[e] = (a.first_iter ? 0 : a.iters[e]) + 1;
+      if (exhausted && a.done) a.done[e] = 1;
+    }
+    if (a.check_convergence && a.done && !legacy) {
       // mpc_wrapper.py:456-467: l2_cost = g*g at the NEW point; stop when last_cost - l2_cost < 1e-3 and sum c^2 < 1e-5
       const float g_new = a.ls_phi[e * NALPHA + best];
       const float c2_new = a.ls_theta[e * NALPHA + best];
@@ -151,6 +187,11 @@ __global__ void select_update_kernel(SelectArgs a) {
     }
   }
   __syncthreads();
+  if (s_stop) {  // the legacy criterion ended the loop: the iterate goes through unchanged
+    for (size_t i = tid; i < nx; i += blockDim.x) { Xo[i] = Xi[i]; Vo[i] = Vi[i]; }
+    for (size_t i = tid; i < nu; i += blockDim.x) Uo[i] = Ui[i];
+    return;
+  }
   const float alpha = s_alpha;
   const float* dX = a.dX + e * nx;
   const float* dU = a.dU + e * nu;
@@ -169,7 +210,7 @@ __global__ void select_update_kernel(SelectArgs a) {
     bad |= !isfinite(uv);
   }
   bad = __syncthreads_or(bad);
-  if (tid == 0 && a.status) a.status[e] = bad ? 1 : 0;
+  if (tid == 0 && a.status) a.status[e] = (bad ? 1 : 0) | (s_idx < 0 ? 2 : 0);
 }
 
 // update_and_extract_helper (mpc_wrapper.py:79-98 / 261-282) and the SRBD shift (mpc_wrapper_srbd.py:135-139)

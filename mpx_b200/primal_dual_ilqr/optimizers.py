@@ -91,7 +91,8 @@ class MpcSolver:
     """One CUDA model handle + workspace for a fixed (config, n_env, lq_mode)."""
 
     def __init__(self, config, n_env, limited_memory=False, device=None, max_iter=1, robot_model=None,
-                 eager_line_search=False, line_search="filter", lq_mode=None, cost_structure="auto"):
+                 eager_line_search=False, line_search="filter", lq_mode=None, cost_structure="auto",
+                 stop_rule="offline"):
         if not torch.cuda.is_available():
             raise RuntimeError("mpx_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
@@ -123,11 +124,19 @@ class MpcSolver:
                    "mpxb_model_set_option")
         # "filter": parallel_filter_line_search (what the reference's mpc runs); "merit": parallel_line_search on the
         # augmented-Lagrangian merit function (optimizers.py:185-217, 295-354, 637-669)
-        if line_search not in ("filter", "merit"):
-            raise ValueError(f"line_search must be 'filter' or 'merit', got {line_search!r}")
-        self.line_search = line_search
-        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_LINE_SEARCH,
-                                                  _lib.LS_MERIT if line_search == "merit" else _lib.LS_FILTER),
+        # "armijo": the legacy solver's sequential backtracking line_search (old_optimazers.py:173-251) on the same 11
+        # step sizes.  stop_rule (max_iter > 1): "offline" = runOffline's rule (mpc_wrapper.py:456-467), "legacy" = the
+        # legacy loop's continuation_criterion (old_optimazers.py:435-447); "legacy" needs "merit" or "armijo"
+        modes = {"filter": _lib.LS_FILTER, "merit": _lib.LS_MERIT, "armijo": _lib.LS_ARMIJO}
+        if line_search not in modes:
+            raise ValueError(f"line_search must be 'filter', 'merit' or 'armijo', got {line_search!r}")
+        if stop_rule not in ("offline", "legacy") or (stop_rule == "legacy" and line_search == "filter"):
+            raise ValueError(f"stop_rule must be 'offline' or 'legacy' (with a merit line search), got {stop_rule!r}")
+        self.line_search, self.stop_rule = line_search, stop_rule
+        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_LINE_SEARCH, modes[line_search]),
+                   "mpxb_model_set_option")
+        _lib.check(self.lib.mpxb_model_set_option(self.handle, _lib.OPT_STOP_RULE,
+                                                  _lib.STOP_LEGACY if stop_rule == "legacy" else _lib.STOP_OFFLINE),
                    "mpxb_model_set_option")
         # cost_structure: "dense" reads the whole weight matrix W; "diagonal" promises a diagonal W and runs the
         # structured kernels (MPXB_OPT_COST_STRUCTURE, csrc/lq3.cuh; whole-body models with limited_memory=True);

@@ -139,3 +139,18 @@ def primal_dual_ilqr(cost, dynamics, x0, X_in, U_in, V_in, max_iterations=100, s
                               merit_slope=float(merit_slope), no_errors=bool(no_errors)))
     no_errors = bool(no_errors) and iteration < max_iterations
     return X, U, V, iteration, g, c, no_errors
+
+
+def legacy_loop_on_problem(pr, reference, parameter, x0, X_in, U_in, V_in, max_iterations, alpha_min=2.0 ** -10, trace=None):
+    """The legacy loop -- sequential Armijo ``line_search``, ``continuation_criterion``, legacy merit slope
+    (old_optimazers.py:154-251, 387-473) -- around the MPC path's Gauss-Newton search direction (optimizers.py:121-184)
+    for one environment of an ``oracle.problems.Problem``.  This is what ``MPXB_LS_ARMIJO`` + ``MPXB_STOP_LEGACY`` run
+    on the device; ``alpha_min = 2^-10`` puts the backtracking on the library's 11 step sizes."""
+    t = lambda a: torch.as_tensor(a, dtype=pr.dtype)
+    reference, parameter, x0, X_in, U_in, V_in = map(t, (reference, parameter, x0, X_in, U_in, V_in))
+    cost = lambda x, u, k: pr.cost(pr.W, reference, x, u, k)
+    hess = lambda x, u, k: pr.hessian_approx(pr.W, reference, x, u, k)
+    dyn = lambda x, u, k: pr.dynamics(x, u, k, parameter)
+    direction = lambda x0_, X, U, V, c: pdi.compute_search_direction(cost, dyn, hess, True, x0_, X, U, V, c)
+    return primal_dual_ilqr(cost, dyn, x0, X_in, U_in, V_in, max_iterations=max_iterations, alpha_min=alpha_min,
+                            direction=direction, trace=trace)
