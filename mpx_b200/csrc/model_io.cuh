@@ -52,7 +52,7 @@ struct TrialOut {
   // second pass of the lazy search: how many environments rejected alpha = 1 decides ON THE DEVICE which of the two
   // whole-body trial kernels does the work (few -> the cooperative one, many -> one warp per trial point); both are
   // launched, the one whose condition fails exits at once.  sel: 0 run, 1 run iff *need_count <= thr, 2 iff > thr
-  int32_t* need_count;
+  int32_t* need_count;   // [1 + E]: count, then the environments that rejected alpha = 1 in arrival order
   int sel, thr;
   // a single-point pass behind alpha = 1 (ia0 > 0, nia == 1) clears need[e] when its point is accepted, so that the
   // remaining points are only evaluated for the environments that reject it as well
@@ -171,7 +171,10 @@ __device__ __forceinline__ void trial_finish(const ModelIO& io, const TrialOut& 
     }
     if (o.need) {
       o.need[e] = nd;
-      if (nd && o.need_count) atomicAdd(o.need_count, 1);  // a count: the order of the increments does not matter
+      // count + compact list of the environments that rejected alpha = 1 (need_count[1..]): the second pass of the
+      // cooperative kernel walks the list instead of all E environments.  The list's order depends on the atomics, the
+      // results do not: every (env, trial point, knot) item writes its own slot
+      if (nd && o.need_count) o.need_count[1 + atomicAdd(o.need_count, 1)] = e;
     }
   }
 }

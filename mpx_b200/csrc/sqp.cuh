@@ -61,7 +61,7 @@ inline WsLayout make_layout(int E, int N, int n, int m, size_t scan_floats, cons
   L.th_part = take(e * NALPHA * (N + 1));
   L.ph_part = take(e * NALPHA * (N + 1));
   L.vc_part = take(e * NALPHA * (N + 1));
-  L.need_count = take(1);  // int32
+  L.need_count = take(1 + e);  // int32: the count, then the list of environments that rejected alpha = 1
   L.ABc = L.PK = L.Kc = L.Pc = L.OKc = 0;
   if (s3) {
     L.ABc = take(e * N * s3->szAB);

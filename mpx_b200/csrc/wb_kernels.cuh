@@ -793,8 +793,12 @@ __global__ void wb_trial_kernel(const WbModel* __restrict__ mdp, ModelIO io, Tri
 // whole_body_interface (mpc_utils.py:275-313): SRBD ground-reaction forces -> joint torques at the whole-body rate.
 // One CTA per environment: qM, qfrc_bias, foot positions and foot Jacobians from the tree stages of the linearise
 // kernel, then  csa = Kp (foot_ref - feet) + Kd (foot_ref_dot - J' qvel),
-//   tau_fb = D[6:] + (M pinv(J') csa)[6:]   with pinv(J') = J (J'J)^-1 (J' has full row rank away from leg singularities;
-//                                            the reference's SVD pinv truncates there, this Cholesky form returns NaN),
+//   tau_fb = D[6:] + (M pinv(J') csa)[6:]   with pinv(J') = J (J'J)^-1 by Cholesky.  J [nv, 3 nc] includes the six
+//                                            floating-base rows, which carry every foot force, so it keeps full column
+//                                            rank where a 3x3 leg Jacobian does not (straight knee: lambda_min(J'J) =
+//                                            0.04 for Aliengo, tests/test_gpu_wbi.py) and the reference's SVD
+//                                            pseudo-inverse (mpc_utils.py:304) equals this left inverse; a J that did
+//                                            lose rank (two feet at one point) would give NaN torques here, in-band,
 //   tau_mpc = -(J grf)[6:],   tau = contact ? tau_mpc : tau_fb   per leg.
 template <int NB, int NV, int NC> struct WbiSmem {
   static constexpr int NF = 3 * NC;
@@ -949,11 +953,15 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
   if (!trial_selected(o)) return;
   // grid-stride over the (env, trial point, knot) items: the first pass launches one CTA per item, the second pass a
   // fixed grid whose CTAs skip the environments that accepted alpha = 1
-  for (int item = blockIdx.x; item < io.E * per_env; item += gridDim.x) {
-  const int e = item / per_env, rem = item - e * per_env;
+  // a later pass (ia0 > 0) walks the compact list of environments that rejected alpha = 1 (trial_finish)
+  const bool listed = o.ia0 > 0 && o.need && o.need_count;
+  const int nenv = listed ? *o.need_count : io.E;
+  for (int item = blockIdx.x; item < nenv * per_env; item += gridDim.x) {
+  const int le = item / per_env, rem = item - le * per_env;
+  const int e = listed ? o.need_count[1 + le] : le;
   const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
   if (io.done && io.done[e]) continue;
-  if (o.ia0 > 0 && o.need && !o.need[e]) continue;  // alpha = 1 was accepted: the smaller steps are never looked at
+  if (o.ia0 > 0 && o.need && !o.need[e]) continue;  // accepted in an earlier pass: the smaller steps are never looked at
   const int n = md.n, m = md.m;
   const bool term = (t == N);
   const float alpha = exp2f(-float(ia));
