@@ -985,19 +985,28 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
   }
   __syncthreads();
-  // ---- cost value: residuals + penalties, then 0.5 (sum_a r_a (W_bb r_b)_a + sum pen)
-  wb_cost_prepare<NV, NC>(md, io, e, t, sm.sx, sm.su, sm.sG, sm.cs, sm.sref, tid, NT);
-  __syncthreads();
-  wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid, NT);
+  // ---- cost value: residuals + penalties, then 0.5 (sum_a r_a (W_bb r_b)_a + sum pen).  It needs x, u and the
+  // reference only, so it runs on warp 1 while warp 0 walks the narrow tree stages S1-S4 (as in the linearise kernel)
   float theta = 0.f, vc = 0.f;
-  if (!term) {
-    wb_tree_fk(md, sm.tr, sm.sx, sm.sx + NQ, tid, NT);
+  if (term) {
+    wb_cost_prepare<NV, NC>(md, io, e, t, sm.sx, sm.su, sm.sG, sm.cs, sm.sref, tid, NT);
     __syncthreads();
-    wb_tree_bodies(md, sm.tr, sm.sx, sm.k.feet, tid, NT);
-    __syncthreads();
-    wb_tree_composite(md, sm.tr, tid, NT);
-    __syncthreads();
-    wb_tree_dofs(md, sm.tr, sm.k.D, tid, NT);
+    wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid, NT);
+  } else {
+    static_assert(NT == 64, "two warps: tree | cost");
+    if (tid < 32) {
+      wb_tree_fk(md, sm.tr, sm.sx, sm.sx + NQ, tid, 32);
+      __syncwarp();
+      wb_tree_bodies(md, sm.tr, sm.sx, sm.k.feet, tid, 32);
+      __syncwarp();
+      wb_tree_composite(md, sm.tr, tid, 32);
+      __syncwarp();
+      wb_tree_dofs(md, sm.tr, sm.k.D, tid, 32);
+    } else {
+      wb_cost_prepare<NV, NC>(md, io, e, t, sm.sx, sm.su, sm.sG, sm.cs, sm.sref, tid - 32, 32);
+      __syncwarp();
+      wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid - 32, 32);
+    }
     __syncthreads();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     __syncthreads();
