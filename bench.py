@@ -358,8 +358,11 @@ def run_native(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # the GPU boxes export NCCL_DEBUG=VERSION (only the banner is printed): raise it to INFO so the communicator
+        # lines ("... rank r nranks N ...", transports, NVLS) reach stderr; a caller's INFO / TRACE setting is kept
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     robot, desc = WORKLOADS[args.workload]
     E, K, Wm = args.envs, args.steps, args.warmup

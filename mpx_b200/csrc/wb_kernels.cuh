@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 // instruction fetch is 15 % of its stall samples; KPB > 1 puts KPB knots -- NT threads, one shared-memory struct and one
 // named barrier each, otherwise independent -- into one CTA, so that a fetched line serves KPB x NT / 32 warps
 #ifndef MPXB_LIN3_KPB
-#define MPXB_LIN3_KPB(NT) ((NT) <= 64 ? 2 : 1)
+#ifndef MPXB_LIN3_KPB64
+#define MPXB_LIN3_KPB64 2
+#endif
+#define MPXB_LIN3_KPB(NT) ((NT) <= 64 ? MPXB_LIN3_KPB64 : 1)
 #endif
 template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF, NDS = 2 * NV + 1;
@@ -941,7 +944,7 @@ template <int NB, int NV, int NC> struct WbTrialSmem {
 };
 
 template <int NB, int NV, int NC, int NT>
-__global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
+__global__ void __launch_bounds__(NT, NT == 32 ? 14 : 8) wb_trial3_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
   using S = WbTrialSmem<NB, NV, NC>;
   constexpr int NQ = NV + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -956,6 +959,11 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
   // a later pass (ia0 > 0) walks the compact list of environments that rejected alpha = 1 (trial_finish)
   const bool listed = o.ia0 > 0 && o.need && o.need_count;
   const int nenv = listed ? *o.need_count : io.E;
+  // NT == 32: one warp per item, every barrier is a warp barrier
+  auto sync = [] {
+    if constexpr (NT == 32) __syncwarp();
+    else __syncthreads();
+  };
   for (int item = blockIdx.x; item < nenv * per_env; item += gridDim.x) {
   const int le = item / per_env, rem = item - le * per_env;
   const int e = listed ? o.need_count[1 + le] : le;
@@ -984,17 +992,18 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     const float* ref = io.reference + (size_t(e) * (N + 1) + t) * md.nref;
     for (int i = tid; i < md.nref; i += NT) sm.sref[i] = ref[i];
   }
-  __syncthreads();
+  sync();
   // ---- cost value: residuals + penalties, then 0.5 (sum_a r_a (W_bb r_b)_a + sum pen).  It needs x, u and the
   // reference only, so it runs on warp 1 while warp 0 walks the narrow tree stages S1-S4 (as in the linearise kernel)
   float theta = 0.f, vc = 0.f;
-  if (term) {
+  if (term || NT == 32) {
     wb_cost_prepare<NV, NC>(md, io, e, t, sm.sx, sm.su, sm.sG, sm.cs, sm.sref, tid, NT);
-    __syncthreads();
+    sync();
     wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid, NT);
-  } else {
-    static_assert(NT == 64, "two warps: tree | cost");
-    if (tid < 32) {
+  }
+  if (!term) {
+    static_assert(NT == 64 || NT == 32, "two warps: tree | cost, or one warp for everything");
+    if (NT == 32 || tid < 32) {
       wb_tree_fk(md, sm.tr, sm.sx, sm.sx + NQ, tid, 32);
       __syncwarp();
       wb_tree_bodies(md, sm.tr, sm.sx, sm.k.feet, tid, 32);
@@ -1007,11 +1016,11 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
       __syncwarp();
       wb_cost_rowsums<NV, NC>(md, io, e, t, sm.cs, tid - 32, 32);
     }
-    __syncthreads();
+    sync();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
-    __syncthreads();
-    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
-    else wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, [] { __syncthreads(); });
+    sync();
+    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+    else wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
     for (int i = tid; i < n; i += NT) {
       const float r = sm.k.xn[i] - sm.sxn[i];
       theta = fmaf(r, r, theta);
@@ -1033,15 +1042,24 @@ __global__ void __launch_bounds__(NT, 8) wb_trial3_kernel(const WbModel* __restr
     phi += __shfl_xor_sync(0xffffffffu, phi, s);
     vc += __shfl_xor_sync(0xffffffffu, vc, s);
   }
-  if ((tid & 31) == 0 && (tid >> 5) < 2) { sm.red[0][tid >> 5] = theta; sm.red[1][tid >> 5] = phi; sm.red[2][tid >> 5] = vc; }
-  __syncthreads();
-  if (tid == 0) {
-    const size_t idx = (size_t(e) * NALPHA + ia) * (N + 1) + t;
-    o.th_part[idx] = sm.red[0][0] + sm.red[0][1];
-    o.ph_part[idx] = 0.5f * (sm.red[1][0] + sm.red[1][1]);
-    if (o.merit) o.vc_part[idx] = sm.red[2][0] + sm.red[2][1];
+  if constexpr (NT == 32) {
+    if (tid == 0) {
+      const size_t idx = (size_t(e) * NALPHA + ia) * (N + 1) + t;
+      o.th_part[idx] = theta;
+      o.ph_part[idx] = 0.5f * phi;
+      if (o.merit) o.vc_part[idx] = vc;
+    }
+  } else {
+    if ((tid & 31) == 0 && (tid >> 5) < 2) { sm.red[0][tid >> 5] = theta; sm.red[1][tid >> 5] = phi; sm.red[2][tid >> 5] = vc; }
+    __syncthreads();
+    if (tid == 0) {
+      const size_t idx = (size_t(e) * NALPHA + ia) * (N + 1) + t;
+      o.th_part[idx] = sm.red[0][0] + sm.red[0][1];
+      o.ph_part[idx] = 0.5f * (sm.red[1][0] + sm.red[1][1]);
+      if (o.merit) o.vc_part[idx] = sm.red[2][0] + sm.red[2][1];
+    }
   }
-  __syncthreads();  // the next item reuses the shared arrays
+  sync();  // the next item reuses the shared arrays
   }
 }
 
@@ -1053,6 +1071,7 @@ inline int wb_class_configure(bool with_interface) {
   bool ok = set(wb_linearize_kernel<NV, NC, MAXD, NT>, sizeof(WbLinSmem<NV, NC, MAXD, NT>));
   ok = ok && set(wb_linearize3_kernel<NB, NV, NC, NI, NT, MPXB_LIN3_KPB(NT)>, MPXB_LIN3_KPB(NT) * sizeof(WbLin3Smem<NB, NV, NC, NI, NT>));
   ok = ok && set(wb_trial3_kernel<NB, NV, NC, 64>, sizeof(WbTrialSmem<NB, NV, NC>));
+  ok = ok && set(wb_trial3_kernel<NB, NV, NC, 32>, sizeof(WbTrialSmem<NB, NV, NC>));
   if (with_interface) {
     if constexpr (NV == 6 + 3 * NC) ok = ok && set(wb_interface_kernel<NB, NV, NC, 64>, sizeof(WbiSmem<NB, NV, NC>));
   }
@@ -1082,11 +1101,14 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
   }
   if (run_coop) {
     to.sel = second ? 1 : 0;
-    constexpr int NT = 64;
+    // one warp per item for the quadrupeds (no CTA barrier, 14 items resident per SM: Go2 x1024 0.71 -> 0.59 ms, r02w);
+    // H1 keeps two warps (6.45 vs 6.75 ms at x4096).  MPXB_TRIAL_NT=32 / 64 forces a form (measurement switch)
+    static const int nt32 = [] { const char* v = getenv("MPXB_TRIAL_NT"); return (v && v[0] == '3') ? 1 : ((v && v[0] == '6') ? 0 : (NV <= 18 ? 1 : 0)); }();
     using S = WbTrialSmem<NB, NV, NC>;
-    auto kern = wb_trial3_kernel<NB, NV, NC, NT>;
     const int items = io.E * to.nia * (io.N + 1);
-    kern<<<(second && items > 148 * 32) ? 148 * 32 : items, NT, sizeof(S), st>>>(dev, io, to);
+    const int grid = (second && items > 148 * 32) ? 148 * 32 : items;
+    if (nt32) wb_trial3_kernel<NB, NV, NC, 32><<<grid, 32, sizeof(S), st>>>(dev, io, to);
+    else wb_trial3_kernel<NB, NV, NC, 64><<<grid, 64, sizeof(S), st>>>(dev, io, to);
     const int wpb = 4;
     trial_reduce_kernel<0><<<(io.E * to.nia + wpb - 1) / wpb, wpb * 32, 0, st>>>(io, to, h.n);
   }
