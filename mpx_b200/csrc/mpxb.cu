@@ -176,8 +176,15 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
   } else {
     int rc = wb_build_model(*d, &mdl->wb_host);
     if (rc != MPXB_OK) { delete mdl; return rc; }
-    if (cudaMalloc(&mdl->wb_dev, sizeof(WbModel)) != cudaSuccess) { delete mdl; return MPXB_ECUDA; }
-    if (cudaMemcpy(mdl->wb_dev, &mdl->wb_host, sizeof(WbModel), cudaMemcpyHostToDevice) != cudaSuccess) {
+    // device image: the model tables, then the work-item table of the folded-tangent stage (wb_build_fold_table)
+    WbFoldTable* ft = new WbFoldTable;
+    wb_build_fold_table(mdl->wb_host, ft);
+    bool up = cudaMalloc(&mdl->wb_dev, sizeof(WbModel) + sizeof(WbFoldTable)) == cudaSuccess;
+    if (!up) { delete ft; delete mdl; return MPXB_ECUDA; }
+    up = cudaMemcpy(mdl->wb_dev, &mdl->wb_host, sizeof(WbModel), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(mdl->wb_dev + 1, ft, sizeof(WbFoldTable), cudaMemcpyHostToDevice) == cudaSuccess;
+    delete ft;
+    if (!up) {
       cudaFree(mdl->wb_dev);
       delete mdl;
       return MPXB_ECUDA;

@@ -153,6 +153,39 @@ inline int wb_build_model(const mpxb_model_desc& d, WbModel* o) {
   return MPXB_OK;
 }
 
+// Work-item table of the folded-tangent stage (wb_tree_fold_coop, F2): the (x-direction, dof) items sorted by the branch
+// they take -- dof moves with the direction | dof is an ancestor | velocity direction | structurally zero -- each
+// segment padded to a multiple of 32 with WB_FOLD_NONE, so every warp runs one branch (the straight (col, dof)
+// enumeration mixes all four in a warp: 14 of 32 lanes active).  Lives in device memory right behind the WbModel.
+constexpr int WB_MAXFOLD = (WB_MAXV + 1 + WB_MAXV) * WB_MAXV + 4 * 32;
+constexpr uint16_t WB_FOLD_NONE = 0xFFFFu;
+struct WbFoldTable {
+  int end_mv, end_anc, end_vel, end_zero;  // segment ends (multiples of 32); item = col << 5 | dof
+  uint16_t item[WB_MAXFOLD];
+};
+inline void wb_build_fold_table(const WbModel& w, WbFoldTable* ft) {
+  memset(ft, 0xFF, sizeof(*ft));
+  const int nq = w.nv + 1, ncol = nq + w.nv;
+  int n = 0;
+  auto type_of = [&](int col, int i) {
+    if (col < 3) return 3;
+    const int D = col - 3, b0 = w.dir_b0[D], nbd = w.dir_nb[D], bi = w.dof_body[i];
+    if (col >= nq) return ((bi >= b0 && bi < b0 + nbd) || ((w.dof_anc[col - nq] >> i) & 1u)) ? 2 : 3;
+    const bool isq = D < 4;
+    if (isq ? (i >= 3) : (bi >= b0 && bi < b0 + nbd)) return 0;
+    return (((isq ? 7u : w.dof_anc[D + 2]) >> i) & 1u) ? 1 : 3;
+  };
+  int ends[4];
+  for (int ty = 0; ty < 4; ++ty) {
+    for (int col = 0; col < ncol; ++col)
+      for (int i = 0; i < w.nv; ++i)
+        if (type_of(col, i) == ty) ft->item[n++] = uint16_t(col << 5 | i);
+    while (n & 31) ft->item[n++] = WB_FOLD_NONE;
+    ends[ty] = n;
+  }
+  ft->end_mv = ends[0]; ft->end_anc = ends[1]; ft->end_vel = ends[2]; ft->end_zero = ends[3];
+}
+
 // ---------------------------------------------------------------- spatial algebra (mjx math)
 template <class TI, class TV, class TO> HD void inert_mul(const TI* I, const TV* v, TO* o) {
   o[0] = I[0] * v[0] + I[3] * v[1] + I[4] * v[2] + (I[7] * v[5] - I[8] * v[4]);

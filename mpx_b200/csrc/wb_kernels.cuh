@@ -663,7 +663,8 @@ __global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
     float* B = o.B + (size_t(e) * N + t) * n * o.ldB;
     // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
     // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
-    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync);
+    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync,
+                      reinterpret_cast<const WbFoldTable*>(mdp + 1));
     sync();
     if (tid < NDS + m) {
       constexpr int FW = S::FW, NF3 = 3 * NC;

@@ -426,7 +426,8 @@ template <int NV> struct WbDirW {
 template <int NB, int NV, int NC, int NI, class Sync>
 HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const float* J, const float* w,
                           const float* a, const float* z, const float* y, const float* grf, const float* wvz,
-                          WbDirW<NV>* dw, float* fold, int FW, int lane, int nl, Sync sync) {
+                          WbDirW<NV>* dw, float* fold, int FW, int lane, int nl, Sync sync,
+                          const WbFoldTable* ft = nullptr) {
   constexpr int NF = 3 * NC, NQ = NV + 1;
   constexpr int npos = 4 + NV - 6, ncol = NQ + NV;
   // F1
@@ -464,7 +465,57 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
   sync();
   // F2
   const int nitem1 = ncol * NV, nitem2 = ncol * NC;
-  for (int it = lane; it < nitem1 + nitem2; it += nl) {
+  if (ft) {
+    // table-driven (col, dof) items: the segments are multiples of 32 items, so a warp runs one branch
+    const int end_mv = ft->end_mv, end_anc = ft->end_anc, end_vel = ft->end_vel, end_zero = ft->end_zero;
+    for (int it = lane; it < end_zero; it += nl) {
+      const unsigned ent = ft->item[it];
+      if (ent == WB_FOLD_NONE) continue;
+      const int col = int(ent >> 5), i = int(ent & 31u);
+      float t1 = 0.f, t2 = 0.f, e = 0.f;
+      if (it < end_anc) {
+        const WbDirW<NV>& d = dw[col];
+        const bool mv = it < end_mv;
+        if (mv) {
+          const float dD = dot6(tr.S[i], tr.g[d.off + md.dof_body[i] - d.b0]);
+          t1 = -(dD + dot6(tr.U[i], d.mu[0]));
+          t2 = -(dD + dot6(tr.U[i], d.mu[1]));
+          e = -dot6(tr.U[i], d.mu[2]);
+        } else {
+          const float dD = dot6(tr.S[i], d.X[0]);
+          t1 = -(dD + dot6(tr.S[i], d.X[1]));
+          t2 = -(dD + dot6(tr.S[i], d.X[2]));
+          e = -dot6(tr.S[i], d.X[3]);
+        }
+        for (int c = 0; c < NC; ++c) {  // foot Jacobian terms of this dof, feet in fixed order
+          const int bc = md.contact_body[c];
+          if (bc < d.b0 || bc >= d.b0 + d.nbd || !((md.contact_dofmask[c] >> i) & 1u)) continue;
+          float dJ[3];
+          if (mv) {
+            cross3(d.Sd, J + i * NF + 3 * c, dJ);
+          } else {
+            float pc[3];
+            cross3(d.Sd, tr.rc[c], pc);
+            for (int k = 0; k < 3; ++k) pc[k] += d.Sd[3 + k];
+            cross3(tr.S[i], pc, dJ);
+          }
+          for (int k = 0; k < 3; ++k) {
+            t2 = fmaf(dJ[k], grf[3 * c + k], t2);
+            e = fmaf(dJ[k], y[3 * c + k], e);
+          }
+        }
+      } else if (it < end_vel) {
+        const int D = col - 3, b0 = md.dir_b0[D], nbd = md.dir_nb[D], off = md.dir_off[D];
+        const int bi = md.dof_body[i];
+        const float s = dot6(tr.S[i], tr.g[(bi >= b0 && bi < b0 + nbd) ? off + bi - b0 : off]);
+        t1 = -s; t2 = -s;
+      }
+      fold[i * FW + col] = t1;
+      fold[(NV + i) * FW + col] = t2;
+      fold[(2 * NV + i) * FW + col] = e;
+    }
+  }
+  for (int it = (ft ? nitem1 + lane : lane); it < nitem1 + nitem2; it += nl) {
     if (it < nitem1) {
       const int col = it / NV, i = it - col * NV;
       float t1 = 0.f, t2 = 0.f, e = 0.f;

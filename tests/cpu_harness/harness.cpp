@@ -102,7 +102,15 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   constexpr int NF = 3 * NC, FW = 2 * NV + 1;
   static WbDirW<NV> dw[NV + 1];
   static float fold[(3 * NV + 2 * NF) * FW];
-  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, 0, 1, nosync);
+  // the device runs the table-driven item order (wb_build_fold_table); both enumerations must fill `fold` identically
+  static WbFoldTable ft;
+  wb_build_fold_table(md, &ft);
+  static float fold_plain[(3 * NV + 2 * NF) * FW];
+  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold_plain, FW, 0, 1, nosync);
+  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, 0, 1, nosync, &ft);
+  for (int r = 0; r < 3 * NV + 2 * NF; ++r)
+    for (int c2 = 0; c2 < nq + nv; ++c2)
+      if (!(fold[r * FW + c2] == fold_plain[r * FW + c2])) return -100;
   std::vector<float> col(n);
   for (int d = 0; d < nq + nv + m; ++d) {
     float t1[NV] = {0};
