@@ -418,7 +418,11 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
       }
       __syncthreads();
       // ---- S4: Cholesky G = L L' in place (lower), one warp; NaN on a non-SPD G propagates like jax cho_factor
-      if (tid < 32) {
+      if constexpr (M <= 32) {
+        // rows in registers, one shuffle per (column, row) pair, no shared-memory traffic inside: the same operations
+        // in the same order as the column form below (bitwise the same factor)
+        if (tid < 32) warp_cholesky<M, LAB>(sG, sgi, tid);
+      } else if (tid < 32) {
         for (int j = 0; j < m; ++j) {
           float d = sG[j * LAB + j];
           for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LAB + k2], sG[j * LAB + k2], d);

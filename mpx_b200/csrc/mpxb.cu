@@ -100,7 +100,12 @@ bool lq3_supported(const Lq3Layout& s) {
 int dispatch_lq3(const Lq3Layout& s, const Lq3Args& a, cudaStream_t st) {
   cudaError_t err = cudaErrorInvalidValue;
   if (s.nh == 37 && s.m == 12) err = launch_lq3<37, 24, 12, 4, 128>(a, st);
-  else if (s.nh == 51 && s.m == 19) err = launch_lq3<51, 24, 19, 0, 128>(a, st);
+  else if (s.nh == 51 && s.m == 19) {
+    // 256 threads (2 CTAs per SM either way: 94 KB of shared memory): H1 x4096 8.39 vs 8.57 ms (r02w); MPXB_LQ3_H1_NT=128 / 256
+    static const int nt256 = [] { const char* v = getenv("MPXB_LQ3_H1_NT"); return (v && v[0] == '1') ? 0 : 1; }();
+    if (a.E == 0) { err = launch_lq3<51, 24, 19, 0, 128>(a, st); if (err == cudaSuccess) err = launch_lq3<51, 24, 19, 0, 256>(a, st); }
+    else err = nt256 ? launch_lq3<51, 24, 19, 0, 256>(a, st) : launch_lq3<51, 24, 19, 0, 128>(a, st);
+  }
   else if (s.nh == 57 && s.m == 46) err = launch_lq3<57, 24, 46, 0, 128>(a, st);
   else return MPXB_EUNSUPPORTED;
   return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA;

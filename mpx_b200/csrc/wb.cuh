@@ -837,31 +837,9 @@ template <int K> HD void wb_tri_solve(const float* Lm, int ld, const float* idL,
 }
 
 #ifdef __CUDACC__
-// Cholesky of a K x K SPD matrix (K <= 32, lower triangle of Mat valid) by ONE warp with the rows in registers: lane i
-// keeps row i, the update is right-looking with one shuffle per (column, row) pair, no barrier and no shared-memory
-// traffic inside.  Every entry sees the same operations in the same order as the shared-memory column form
-// (s = M_ik - sum_j L_ij L_kj, j ascending, fmaf(-a, b, s); L_ij = s / sqrt(pivot)), so the factor is bitwise the same.
-// Writes the strictly-lower factor back into Mat and the reciprocal diagonal into dinv.
-template <int K, int LD>
-__device__ __forceinline__ void wb_warp_cholesky(float* Mat, float* dinv, int lane) {
-  static_assert(K <= 32, "one row per lane");
-  float row[K];
-  const int r = lane < K ? lane : K - 1;  // spare lanes mirror the last row; their results are discarded
-#pragma unroll
-  for (int c = 0; c < K; ++c) row[c] = (c <= r) ? Mat[r * LD + c] : 0.f;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    const float sjj = __shfl_sync(0xffffffffu, row[j], j);
-    const float dj = 1.f / sqrtf(sjj);
-    const float lij = row[j] * dj;
-    if (lane == j) dinv[j] = dj;
-    if (lane > j && lane < K) Mat[lane * LD + j] = lij;
-#pragma unroll
-    for (int c = j + 1; c < K; ++c) {
-      const float lcj = __shfl_sync(0xffffffffu, lij, c);
-      row[c] = fmaf(-lij, lcj, row[c]);
-    }
-  }
+// one-warp register Cholesky: common.cuh (warp_cholesky), shared with the LQ kernel
+template <int K, int LD> __device__ __forceinline__ void wb_warp_cholesky(float* Mat, float* dinv, int lane) {
+  warp_cholesky<K, LD>(Mat, dinv, lane);
 }
 #endif
 
