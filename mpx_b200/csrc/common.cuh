@@ -179,6 +179,20 @@ HD float penalty_dd(float c, float alpha, float sigma) {
   return dd;
 }
 
+// 1 / sqrt(d) of a Cholesky pivot.  Device: hardware reciprocal square root + one Newton step (about 1 ulp) -- IEEE
+// sqrt followed by an IEEE divide is ~120 cycles longer per pivot and the pivots are the serial chain of every
+// factorisation here; a pivot d <= 0 (or NaN) gives NaN, so a non-SPD matrix still shows up in-band like jax
+// cho_factor.  Host (tests/cpu_harness): 1 / sqrtf.
+HD float chol_pivot_inv(float d) {
+#ifdef __CUDA_ARCH__
+  float inv = rsqrtf(d);
+  inv = inv * fmaf(-0.5f * d, inv * inv, 1.5f);
+  return (d > 0.f) ? inv : __int_as_float(0x7fc00000);
+#else
+  return 1.f / sqrtf(d);
+#endif
+}
+
 #ifdef __CUDACC__
 // Cholesky of a K x K SPD matrix (K <= 32, lower triangle of Mat valid) by ONE warp with the rows in registers: lane i
 // keeps row i, the update is right-looking with one shuffle per (column, row) pair, no barrier and no shared-memory
@@ -195,7 +209,7 @@ __device__ __forceinline__ void warp_cholesky(float* Mat, float* dinv, int lane)
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const float sjj = __shfl_sync(0xffffffffu, row[j], j);
-    const float dj = 1.f / sqrtf(sjj);
+    const float dj = chol_pivot_inv(sjj);
     const float lij = row[j] * dj;
     if (lane == j) dinv[j] = dj;
     if (lane > j && lane < K) Mat[lane * LD + j] = lij;

@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(NT, lq_rt_min_blocks<n, m>()) lq_seq_kernel(Lq
       for (int j = 0; j < m; ++j) {
         float d = sG[j * LM + j];
         for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LM + k2], sG[j * LM + k2], d);
-        const float inv = 1.f / sqrtf(d);
+        const float inv = chol_pivot_inv(d);
         __syncwarp();
         if (tid == 0) sgi[j] = inv;
         for (int i = j + 1 + tid; i < m; i += 32) {

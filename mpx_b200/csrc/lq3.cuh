@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
           float d = L[j * (j + 1) / 2 + j];
 #pragma unroll
           for (int k2 = 0; k2 < j; ++k2) d = fmaf(-L[j * (j + 1) / 2 + k2], L[j * (j + 1) / 2 + k2], d);
-          const float inv = 1.f / sqrtf(d);
+          const float inv = chol_pivot_inv(d);
           gi[j] = inv;
 #pragma unroll
           for (int i = j + 1; i < M; ++i) {
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
         for (int j = 0; j < m; ++j) {
           float d = sG[j * LAB + j];
           for (int k2 = 0; k2 < j; ++k2) d = fmaf(-sG[j * LAB + k2], sG[j * LAB + k2], d);
-          const float inv = 1.f / sqrtf(d);
+          const float inv = chol_pivot_inv(d);
           __syncwarp();
           if (tid == 0) sgi[j] = inv;
           for (int i = j + 1 + tid; i < m; i += 32) {

@@ -7,12 +7,14 @@
 // There is no host synchronisation and no allocation on this path.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
 
 #include "../../include/mpxb.h"
 #include "lq.cuh"
+#include "lq_small.cuh"
 #include "sqp.cuh"
 #include "srbd_kernels.cuh"
 #include "wb_launch.h"
@@ -56,8 +58,21 @@ struct DeviceGuard {
 
 namespace {
 
+constexpr size_t MPXB_LQ_SMALL_MAX_BYTES = 232448 - 1024;  // 227 KB of shared memory per CTA on sm_100
+
 template <int n, int m> cudaError_t launch_lq_seq(const LqArgs& a, cudaStream_t st) {
   constexpr int NT = 256;
+  if constexpr (n <= 16 && m <= 16) {
+    // small systems (SRBD): the whole horizon in shared memory, no global traffic inside the time loop (lq_small.cuh);
+    // the streaming kernel below takes over when the horizon does not fit.  MPXB_LQ_SMALL=0: measurement switch
+    static const int off = [] { const char* v = getenv("MPXB_LQ_SMALL"); return (v && v[0] == '0') ? 1 : 0; }();
+    const size_t bytes = lq_small_bytes<n, m>(a.N);
+    // one CTA per SM: up to ~6 waves it beats the streaming kernel's four resident CTAs (E = 296: 0.14 vs 0.24 ms)
+    if (!off && bytes <= MPXB_LQ_SMALL_MAX_BYTES && a.E <= 6 * 148) {
+      lq_small_kernel<n, m, NT><<<a.E, NT, bytes, st>>>(a);
+      return cudaGetLastError();
+    }
+  }
   auto kern = lq_seq_kernel<n, m, NT>;
   kern<<<a.E, NT, lq_rt_bytes<n, m>(a.nzc), st>>>(a);
   return cudaGetLastError();
@@ -67,6 +82,10 @@ template <int n, int m> cudaError_t launch_lq_seq(const LqArgs& a, cudaStream_t 
 // mutable global state and a captured launch sequence contains launches only.
 template <int n, int m> cudaError_t configure_lq() {
   cudaError_t err = cudaFuncSetAttribute(lq_seq_kernel<n, m, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lq_rt_bytes<n, m>(0)));
+  if constexpr (n <= 16 && m <= 16) {
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(lq_small_kernel<n, m, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(MPXB_LQ_SMALL_MAX_BYTES));
+  }
   if (err == cudaSuccess) err = configure_lq_scan<n, m>();
   if (err == cudaSuccess) err = configure_lq_pscan<n, m>();
   return err;

@@ -888,7 +888,7 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
   for (int j = 0; j < nv; ++j) {
     float sjj = k.M[j * NV + j];
     for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
-    const float dj = 1.f / sqrtf(sjj);
+    const float dj = chol_pivot_inv(sjj);
     for (int i = j + 1 + lane; i < nv; i += nl) {
       float s = k.M[i * NV + j];
       for (int p = 0; p < j; ++p) s = fmaf(-k.M[i * NV + p], k.M[j * NV + p], s);
@@ -944,7 +944,7 @@ HD void wb_s3_primal(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const
     for (int j = 0; j < nf; ++j) {
       float sjj = k.JMJ[j * NF + j];
       for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
-      const float dj = 1.f / sqrtf(sjj);
+      const float dj = chol_pivot_inv(sjj);
       for (int i = j + 1 + lane; i < nf; i += nl) {
         float s = k.JMJ[i * NF + j];
         for (int p = 0; p < j; ++p) s = fmaf(-k.JMJ[i * NF + p], k.JMJ[j * NF + p], s);
@@ -1044,7 +1044,7 @@ HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, c
   for (int j = 0; j < nv; ++j) {
     float sjj = k.M[j * NV + j];
     for (int p = 0; p < j; ++p) sjj = fmaf(-k.M[j * NV + p], k.M[j * NV + p], sjj);
-    const float dj = 1.f / sqrtf(sjj);
+    const float dj = chol_pivot_inv(sjj);
     for (int i = j + 1 + lane; i < nv; i += nl) {
       float s = k.M[i * NV + j];
       for (int p = 0; p < j; ++p) s = fmaf(-k.M[i * NV + p], k.M[j * NV + p], s);
@@ -1114,7 +1114,7 @@ HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, c
     for (int j = 0; j < nf; ++j) {
       float sjj = k.JMJ[j * NF + j];
       for (int p = 0; p < j; ++p) sjj = fmaf(-k.JMJ[j * NF + p], k.JMJ[j * NF + p], sjj);
-      const float dj = 1.f / sqrtf(sjj);
+      const float dj = chol_pivot_inv(sjj);
       for (int i = j + 1 + lane; i < nf; i += nl) {
         float s = k.JMJ[i * NF + j];
         for (int p = 0; p < j; ++p) s = fmaf(-k.JMJ[i * NF + p], k.JMJ[j * NF + p], s);

@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(NT) wb_interface_kernel(const WbModel* __restr
     for (int j = 0; j < NF; ++j) {
       float d = sm.G[j * NF + j];
       for (int p = 0; p < j; ++p) d = fmaf(-sm.G[j * NF + p], sm.G[j * NF + p], d);
-      const float inv = 1.f / sqrtf(d);
+      const float inv = chol_pivot_inv(d);
       sm.gi[j] = inv;
       for (int i = j + 1; i < NF; ++i) {
         float v = sm.G[i * NF + j];

@@ -41,6 +41,11 @@ _LQ_COST_US = {13: (8.9, 15.3, 24.5, 1.2), 61: (18.0, 92.6, 64.0, 2.7), 75: (30.
                81: (79.0, 158.6, 230.0, 4.1)}
 
 
+# the small-system sequential kernel (csrc/lq_small.cuh, SRBD): 71 us for N = 25 at E = 1 (r02w); it holds the whole
+# horizon in shared memory, which for n = 13, m = 12 fits up to N = 47
+_LQ_SMALL_KNOT_US, _LQ_SMALL_MAX_N = 2.9, 47
+
+
 LQ_MODE_NAMES = {_lib.LQ_SEQUENTIAL: "sequential", _lib.LQ_SCAN: "scan", _lib.LQ_SCAN_SERIAL: "scan_serial",
                  _lib.LQ_SCAN_PARALLEL: "scan_parallel"}
 
@@ -66,8 +71,8 @@ def wrapper_lq_mode(limited_memory, n_env, n, N):
     * ``limited_memory=False`` -> the scan scheduled in parallel over the horizon (one CTA per knot, log2 levels) when
       its modelled time  fixed + levels x waves x combine  beats  N x knot  of the sequential kernel, with the
       per-size constants measured at E = 1 (``_LQ_COST_US``; waves = ceil(n_env (N + 1) / 148)): single instances of
-      the SRBD model (tick 0.18 vs 0.28 ms) and of Talos (N = 25: LQ 1.04 vs 1.99 ms; N = 200: 3.7 vs 15.3 ms), long
-      horizons in general; Aliengo / Go2 at N = 25 (0.56 vs 0.45 ms), H1 (0.77 vs 0.76 ms) and every large batch stay on the sequential
+      Talos (N = 25: LQ 1.04 vs 1.99 ms; N = 200: 3.7 vs 15.3 ms), long horizons in general (the SRBD model beyond
+      N = 47; up to there its sequential solve runs in the small-system kernel, LQ 0.07 vs 0.13 ms); Aliengo / Go2 at N = 25 (0.56 vs 0.45 ms), H1 (0.77 vs 0.76 ms) and every large batch stay on the sequential
       kernel, where one CTA per environment already fills the GPU and the scan's ~9x FLOPs buy nothing.
 
     ``MPXB_LQ=scan`` in the environment restores the literal mapping (``LQ_SCAN``), ``MPXB_LQ=sequential`` forces the
@@ -80,6 +85,8 @@ def wrapper_lq_mode(limited_memory, n_env, n, N):
     if forced == "sequential" or limited_memory or n_env > 64 or n not in _LQ_COST_US:
         return _lib.LQ_SEQUENTIAL
     knot, comb, fixed, roll = _LQ_COST_US[n]
+    if n == 13 and N <= _LQ_SMALL_MAX_N:
+        knot = _LQ_SMALL_KNOT_US  # whole horizon in shared memory (csrc/lq_small.cuh)
     levels = int(N).bit_length()
     waves = -(-n_env * (N + 1) // _sm_count())
     t_scan = fixed + roll * N + levels * waves * comb

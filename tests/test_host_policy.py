@@ -22,11 +22,12 @@ def test_wrapper_lq_mode_policy(monkeypatch):
     assert wrapper_lq_mode(True, 1, 81, 200) == _lib.LQ_SEQUENTIAL
     assert wrapper_lq_mode(True, 1024, 61, 25) == _lib.LQ_SEQUENTIAL
     # limited_memory=False: the parallel scan where it was measured faster ...
-    assert wrapper_lq_mode(False, 1, 13, 25) == _lib.LQ_SCAN_PARALLEL      # Aliengo SRBD single instance
+    assert wrapper_lq_mode(False, 1, 13, 100) == _lib.LQ_SCAN_PARALLEL     # Aliengo SRBD, horizon beyond the small kernel
     assert wrapper_lq_mode(False, 1, 81, 25) == _lib.LQ_SCAN_PARALLEL      # Talos
     assert wrapper_lq_mode(False, 1, 81, 200) == _lib.LQ_SCAN_PARALLEL     # Talos, long horizon
     assert wrapper_lq_mode(False, 1, 61, 100) == _lib.LQ_SCAN_PARALLEL     # barrel-roll horizon
     # ... and the sequential kernel elsewhere
+    assert wrapper_lq_mode(False, 1, 13, 25) == _lib.LQ_SEQUENTIAL         # Aliengo SRBD single instance (lq_small kernel)
     assert wrapper_lq_mode(False, 1, 61, 25) == _lib.LQ_SEQUENTIAL         # Aliengo whole-body single instance
     assert wrapper_lq_mode(False, 1, 75, 25) == _lib.LQ_SEQUENTIAL         # H1
     assert wrapper_lq_mode(False, 1024, 61, 25) == _lib.LQ_SEQUENTIAL      # large batches
