@@ -1092,7 +1092,13 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
   const bool second = to.ia0 > 0 && to.need_count != nullptr;
   const bool run_warp = !coop_ok || second || to.nia == NALPHA;
   const bool run_coop = coop_ok && to.nia != NALPHA;
-  to.thr = io.E / 8;
+  // second pass: the warp form (one warp per trial point, serial over the knots) pays off only when the rejecting
+  // environments alone fill the GPU; up to a grid's worth of cooperative items (148 x 32 CTAs) the cooperative form
+  // runs whatever the count -- a single instance that rejects alpha = 1 took 0.4 ms extra in the warp form
+  {
+    const int coop_envs = (148 * 32) / ((NALPHA - 1) * (io.N + 1));
+    to.thr = io.E / 8 > coop_envs ? io.E / 8 : coop_envs;
+  }
   if (run_warp) {
     to.sel = (second && coop_ok) ? 2 : 0;
     const int wpb = 2;
