@@ -1188,6 +1188,115 @@ HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, c
   sync();
 }
 
+// Primal contact solve for TRIAL evaluations (device only): nothing but x+ = f(x, u) is wanted, so neither qM^-1 nor
+// M^-1 J is ever formed.  With qM = L L' and the forward substitutions  Y = L^-1 J,  u = L^-1 (tau - D):
+//   J' M^-1 J = Y' Y,   J' M^-1 (tau - D) = Y' u,   qacc = L^-T (u + Y grf)
+// i.e. one forward substitution per column (NF + 1 workers, registers), two small products and ONE backward
+// substitution, done by a warp with the vector spread over its lanes -- about a third of the operations of the
+// explicit-inverse route the linearise kernel takes (there every later derivative column re-uses qM^-1).
+// Same quantities as wb_s3_primal / wb_s3_primal_inv up to rounding.
+#ifdef __CUDACC__
+template <int NV, int NC, class Sync>
+__device__ __forceinline__ void wb_s3_primal_fwd(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u,
+                                                 const float* contact, int lane, int nl, Sync sync) {
+  constexpr int NF = 3 * NC;
+  constexpr int nv = NV, nj = NV - 6, nf = NF;
+  static_assert(NV <= 32 && NF <= 32, "one warp: a lane per row");
+  const float* qvel = x + 7 + nj;
+  for (int i = lane; i < nv; i += nl) k.tmd[i] = (i < 6 ? 0.f : u[i - 6]) - k.D[i];
+  sync();
+  if (lane < 32) wb_warp_cholesky<NV, NV>(k.M, k.dL, lane);
+  sync();
+  // Y = L^-1 J (columns 0..nf-1, into MiJ), u = L^-1 tmd (column nf, into w)
+  for (int c = lane; c <= nf; c += nl) {
+    float y[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float sacc = (c < nf) ? k.J[i * NF + c] : k.tmd[i];
+#pragma unroll
+      for (int p = 0; p < i; ++p) sacc = fmaf(-k.M[i * NV + p], y[p], sacc);
+      y[i] = sacc * k.dL[i];
+    }
+    if (c < nf) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) k.MiJ[i * NF + c] = y[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) k.w[i] = y[i];
+    }
+  }
+  sync();
+  for (int idx = lane; idx < nf * nf + nf; idx += nl) {
+    if (idx < nf * nf) {
+      const int a = idx / nf, b = idx - a * nf;
+      if (b <= a) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < nv; ++i) sacc = fmaf(k.MiJ[i * NF + a], k.MiJ[i * NF + b], sacc);
+        if (a == b) sacc += md.reg;
+        k.JMJ[a * NF + b] = sacc;
+      }
+    } else {
+      const int a = idx - nf * nf;
+      float sacc = 0.f, sv = 0.f;
+#pragma unroll
+      for (int i = 0; i < nv; ++i) {
+        sacc = fmaf(k.MiJ[i * NF + a], k.w[i], sacc);
+        sv = fmaf(k.J[i * NF + a], qvel[i], sv);
+      }
+      k.yr[a] = -(sacc + 2.f * md.alpha * sv);
+    }
+  }
+  sync();
+  if (lane < 32) wb_warp_cholesky<NF, NF>(k.JMJ, k.dLc, lane);
+  sync();
+  if (lane == 0) {
+    float yy[NF];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) yy[c] = k.yr[c];
+    wb_tri_solve<NF>(k.JMJ, NF, k.dLc, yy);
+#pragma unroll
+    for (int c = 0; c < NF; ++c) { k.y[c] = yy[c]; k.grf[c] = yy[c] * contact[c / 3]; }
+  }
+  sync();
+  // qacc = L^-T (u + Y grf): backward substitution across the lanes of warp 0 (lane i holds entry i)
+  if (lane < 32) {
+    float zi = 0.f;
+    if (lane < nv) {
+      zi = k.w[lane];
+#pragma unroll
+      for (int c = 0; c < nf; ++c) zi = fmaf(k.MiJ[lane * NF + c], k.grf[c], zi);
+    }
+    float ai = 0.f;
+#pragma unroll
+    for (int i = NV - 1; i >= 0; --i) {
+      const float xi = __shfl_sync(0xffffffffu, zi, i) * k.dL[i];
+      if (lane == i) ai = xi;
+      if (lane < i) zi = fmaf(-k.M[i * NV + lane], xi, zi);
+    }
+    if (lane < nv) k.a[lane] = ai;
+  }
+  sync();
+  // semi-implicit Euler step (as the tail of wb_s3_primal_inv, TANGENT = false)
+  const float dt = md.dt;
+  float* vn = k.xn + 7 + nj;
+  for (int i = lane; i < nv; i += nl) vn[i] = qvel[i] + k.a[i] * dt;
+  sync();
+  for (int i = lane; i < 3; i += nl) k.xn[i] = x[i] + vn[i] * dt;
+  for (int i = lane; i < nj; i += nl) k.xn[7 + i] = x[7 + i] + vn[6 + i] * dt;
+  for (int i = lane; i < nf; i += nl) {
+    k.xn[7 + nj + nv + i] = k.feet[i];
+    if (md.grf_as_state) k.xn[7 + nj + nv + nf + i] = k.grf[i];
+  }
+  if (lane == 0) {
+    float qo[4];
+    quat_integrate(x + 3, vn + 3, dt, qo);
+    for (int r = 0; r < 4; ++r) k.xn[3 + r] = qo[r];
+  }
+  sync();
+}
+#endif
+
 // wb_s3_tangent on what wb_s3_primal_inv leaves: k.M = qM^-1 (explicit), k.JMJ / k.dLc = Cholesky factor of J'M^-1J
 template <int NV, int NC, class V1, class V2, class Out>
 HD void wb_s3_tangent_inv(const WbModel& md, const WbKnot<NV, NC>& k, const float* contact, int is_u, int dir, V1 t1, V2 t2,

@@ -1020,8 +1020,13 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 8) wb_trial3_kernel(const 
     sync();
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     sync();
-    if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
-    else wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+    // robots with a contact solve: forward substitutions only (wb_s3_primal_fwd); Talos (GRFs are controls): one solve
+    if constexpr (NV <= MPXB_INV_MAXNV) {
+      if (md.contact_solve) wb_s3_primal_fwd<NV, NC>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+      else wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+    } else {
+      wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+    }
     for (int i = tid; i < n; i += NT) {
       const float r = sm.k.xn[i] - sm.sxn[i];
       theta = fmaf(r, r, theta);
