@@ -530,9 +530,10 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 //   S7  thread d: folded tangents of direction d (analytic) -> column d of [A | B] (wb_s3_tangent), A'V / B'V
 //   P5  cost gradient, q, r, Gauss-Newton blocks
 // resident CTAs per SM the register allocation is tuned for (measured on B200, Go2 x1024: 6 CTAs of 64 threads at
-// 168 registers beat both 4 at 255 and 8 at 128)
+// 168 registers beat both 4 at 255 and 8 at 128; H1 x4096: 4 CTAs of 128 threads at 128 registers -- 16 warps per SM,
+// no spills -- 11.5 ms vs 12.3 ms for 4 x 96 threads at 168 and 14.7 ms for 3 x 128 at 168, r02y)
 #ifndef MPXB_LIN3_MINB
-#define MPXB_LIN3_MINB (NT <= 64 ? 6 : (NT <= 96 ? 4 : 2))
+#define MPXB_LIN3_MINB (NT <= 64 ? 6 : (NT <= 96 ? 4 : (NV <= 25 ? 4 : 2)))
 #endif
 // knots per CTA: the kernel is ~16 k SASS instructions of straight-line code that every CTA executes once, and
 // instruction fetch is 15 % of its stall samples; KPB > 1 puts KPB knots -- NT threads, one shared-memory struct and one
