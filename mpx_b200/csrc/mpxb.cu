@@ -116,15 +116,28 @@ bool lq3_supported(const Lq3Layout& s) {
   return (s.nh == 37 && s.ntl == 24 && s.m == 12 && s.ncone == 4) || (s.nh == 51 && s.ntl == 24 && s.m == 19 && s.ncone == 0) ||
          (s.nh == 57 && s.ntl == 24 && s.m == 46 && s.ncone == 0);
 }
+// threads per CTA of the structured LQ kernel: the first of NTS... is the default, MPXB_LQ3_NT=<n> selects another
+// instantiated count (measurement switch); a.E == 0 configures every instantiation (mpxb_model_create)
+template <int NH, int NTL, int M, int NCONE, int... NTS> cudaError_t launch_lq3_nt(const Lq3Args& a, cudaStream_t st) {
+  static const int want = [] { const char* v = getenv("MPXB_LQ3_NT"); return v ? atoi(v) : 0; }();
+  constexpr int nts[] = {NTS...};
+  int pick = nts[0];
+  for (int x : nts) if (x == want) pick = x;
+  cudaError_t err = cudaSuccess;
+  if (a.E == 0) {
+    ((err = (err == cudaSuccess) ? launch_lq3<NH, NTL, M, NCONE, NTS>(a, st) : err), ...);
+    return err;
+  }
+  ((pick == NTS ? (void)(err = launch_lq3<NH, NTL, M, NCONE, NTS>(a, st)) : (void)0), ...);
+  return err;
+}
 int dispatch_lq3(const Lq3Layout& s, const Lq3Args& a, cudaStream_t st) {
   cudaError_t err = cudaErrorInvalidValue;
-  if (s.nh == 37 && s.m == 12) err = launch_lq3<37, 24, 12, 4, 128>(a, st);
-  else if (s.nh == 51 && s.m == 19) {
-    // 256 threads (2 CTAs per SM either way: 94 KB of shared memory): H1 x4096 8.39 vs 8.57 ms (r02w); MPXB_LQ3_H1_NT=128 / 256
-    static const int nt256 = [] { const char* v = getenv("MPXB_LQ3_H1_NT"); return (v && v[0] == '1') ? 0 : 1; }();
-    if (a.E == 0) { err = launch_lq3<51, 24, 19, 0, 128>(a, st); if (err == cudaSuccess) err = launch_lq3<51, 24, 19, 0, 256>(a, st); }
-    else err = nt256 ? launch_lq3<51, 24, 19, 0, 256>(a, st) : launch_lq3<51, 24, 19, 0, 128>(a, st);
-  }
+  // Go2 / Aliengo: 4 CTAs of 128 threads per SM (51 KB each; x1024: 0.888 ms, 96 threads 0.893, 160 threads 0.951).
+  // H1 (94 KB, 2 CTAs per SM): 192 threads at 168 registers, x4096: 7.32 ms vs 7.56 (160), 8.05 (256 threads at the
+  // 128-register cap), 8.20 (128) and 8.27 (224), r02y
+  if (s.nh == 37 && s.m == 12) err = launch_lq3_nt<37, 24, 12, 4, 128, 96>(a, st);
+  else if (s.nh == 51 && s.m == 19) err = launch_lq3_nt<51, 24, 19, 0, 192, 128, 256>(a, st);
   else if (s.nh == 57 && s.m == 46) err = launch_lq3<57, 24, 46, 0, 128>(a, st);
   else return MPXB_EUNSUPPORTED;
   return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA;

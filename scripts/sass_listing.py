@@ -13,10 +13,12 @@ kernels = {
     "lq_seq_13_12": "_ZN4mpxb13lq_seq_kernelILi13ELi12ELi256EEEvNS_6LqArgsE",
     "lq_scan_61_12": "_ZN4mpxb14lq_scan_kernelILi61ELi12ELi256EEEvNS_6LqArgsE",
     "lq3_go2": "_ZN4mpxb10lq3_kernelILi37ELi24ELi12ELi4ELi128EEEvNS_7Lq3ArgsE",
-    "lq3_h1": "_ZN4mpxb10lq3_kernelILi51ELi24ELi19ELi0ELi128EEEvNS_7Lq3ArgsE",
+    "lq3_h1": "_ZN4mpxb10lq3_kernelILi51ELi24ELi19ELi0ELi192EEEvNS_7Lq3ArgsE",
+    "lq_small_13_12": "_ZN4mpxb15lq_small_kernelILi13ELi12ELi256EEEvNS_6LqArgsE",
     "wb_linearize3_quad": "_ZN4mpxb20wb_linearize3_kernelILi14ELi18ELi4ELi192ELi64ELi2EEEvPKNS_7WbModelENS_7ModelIOENS_6LinOutE",
-    "wb_linearize3_h1": "_ZN4mpxb20wb_linearize3_kernelILi21ELi25ELi4ELi320ELi96ELi1EEEvPKNS_7WbModelENS_7ModelIOENS_6LinOutE",
-    "wb_trial3_quad": "_ZN4mpxb16wb_trial3_kernelILi14ELi18ELi4ELi64EEEvPKNS_7WbModelENS_7ModelIOENS_8TrialOutE",
+    "wb_linearize3_h1": "_ZN4mpxb20wb_linearize3_kernelILi21ELi25ELi4ELi320ELi128ELi1EEEvPKNS_7WbModelENS_7ModelIOENS_6LinOutE",
+    "wb_trial3_quad": "_ZN4mpxb16wb_trial3_kernelILi14ELi18ELi4ELi32EEEvPKNS_7WbModelENS_7ModelIOENS_8TrialOutE",
+    "wb_trial3_h1": "_ZN4mpxb16wb_trial3_kernelILi21ELi25ELi4ELi64EEEvPKNS_7WbModelENS_7ModelIOENS_8TrialOutE",
     "srbd_linearize": "_ZN4mpxb21srbd_linearize_kernelENS_10SrbdParamsENS_7ModelIOENS_6LinOutE",
     "select_update": "_ZN4mpxb20select_update_kernelENS_10SelectArgsE",
     "pscan_combine_81": "_ZN4mpxb20pscan_combine_kernelILi81ELi512EEEviiPKiNS_8PscanBufES3_",
