@@ -852,7 +852,7 @@ template <int K, int LD> __device__ __forceinline__ void wb_warp_cholesky(float*
 #endif
 
 // Per-knot primal workspace of the analytic contact solve (shared memory in the kernel)
-template <int NV, int NC> struct WbKnot {
+template <int NV, int NC, bool INV = true> struct WbKnot {
   static constexpr int NF = 3 * NC, NX = 13 + 2 * (NV - 6) + 2 * NF;
   float M[NV * NV];      // qM -> strictly-lower Cholesky factor in place (diagonal in dL)
   float J[NV * NF], MiJ[NV * NF], JMJ[NF * NF];
@@ -863,7 +863,8 @@ template <int NV, int NC> struct WbKnot {
   float y[NF], grf[NF], feet[NF];
   float xn[NX], Gq[16], Gw[12];
   // explicit-inverse variant (NV <= MPXB_INV_MAXNV): L^-1 and the right-hand side of the GRF solve
-  float Li[NV <= MPXB_INV_MAXNV ? NV * NV : NV], yr[NF];
+  // (INV = false: trial items, which never form the inverse -- wb_s3_primal_fwd)
+  float Li[(INV && NV <= MPXB_INV_MAXNV) ? NV * NV : NV], yr[NF];
 };
 
 // Cooperative primal contact solve (models.py:93-115 / 146-167 / 206-215): `lane` of `nl` workers, `sync()` between
@@ -1196,8 +1197,8 @@ HD void wb_s3_primal_inv(const WbModel& md, WbKnot<NV, NC>& k, const float* x, c
 // explicit-inverse route the linearise kernel takes (there every later derivative column re-uses qM^-1).
 // Same quantities as wb_s3_primal / wb_s3_primal_inv up to rounding.
 #ifdef __CUDACC__
-template <int NV, int NC, class Sync>
-__device__ __forceinline__ void wb_s3_primal_fwd(const WbModel& md, WbKnot<NV, NC>& k, const float* x, const float* u,
+template <int NV, int NC, class Knot, class Sync>
+__device__ __forceinline__ void wb_s3_primal_fwd(const WbModel& md, Knot& k, const float* x, const float* u,
                                                  const float* contact, int lane, int nl, Sync sync) {
   constexpr int NF = 3 * NC;
   constexpr int nv = NV, nj = NV - 6, nf = NF;

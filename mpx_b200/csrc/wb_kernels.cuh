@@ -939,14 +939,22 @@ inline int wb_class_linearize(const WbModel& h, const WbModel* dev, const ModelI
 // are summed by trial_reduce_kernel.
 template <int NB, int NV, int NC> struct WbTrialSmem {
   static constexpr int NJ = NV - 6, NF = 3 * NC, NX = 13 + 2 * NJ + 2 * NF, NU = NJ + NF;
-  WbKnot<NV, NC> k;
+  WbKnot<NV, NC, (NV > MPXB_INV_MAXNV)> k;   // the quadruped / H1 trial solve forms no inverse: no L^-1 buffer
   WbTree<NB, NV, NC, 1> tr;
   WbCostSmem<NV, NC> cs;
   float sx[NX], su[NU], sxn[NX], svn[NX], sref[13 + NJ + 7 * NC], sG[12], red[3][2];
 };
 
+// resident CTAs per SM the register allocation aims at: what shared memory allows, at most 16 one-warp items resp.
+// 8 two-warp items (128 registers per thread either way)
+template <int NB, int NV, int NC, int NT> __host__ __device__ constexpr int wb_trial_min_blocks() {
+  constexpr int cap = NT == 32 ? 16 : 8;
+  constexpr int fit = int(232448 / (sizeof(WbTrialSmem<NB, NV, NC>) + 1024));
+  return fit < 1 ? 1 : (fit > cap ? cap : fit);
+}
+
 template <int NB, int NV, int NC, int NT>
-__global__ void __launch_bounds__(NT, NT == 32 ? 14 : 8) wb_trial3_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
+__global__ void __launch_bounds__(NT, wb_trial_min_blocks<NB, NV, NC, NT>()) wb_trial3_kernel(const WbModel* __restrict__ mdp, ModelIO io, TrialOut o) {
   using S = WbTrialSmem<NB, NV, NC>;
   constexpr int NQ = NV + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1022,9 +1030,9 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 8) wb_trial3_kernel(const 
     wb_tree_mass_jac(md, sm.tr, sm.k.M, sm.k.J, tid, NT);
     sync();
     // robots with a contact solve: forward substitutions only (wb_s3_primal_fwd); Talos (GRFs are controls): one solve
+    // (the launcher sends a model of these classes without a contact solve to the warp form)
     if constexpr (NV <= MPXB_INV_MAXNV) {
-      if (md.contact_solve) wb_s3_primal_fwd<NV, NC>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
-      else wb_s3_primal_inv<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
+      wb_s3_primal_fwd<NV, NC>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
     } else {
       wb_s3_primal<NV, NC, false>(md, sm.k, sm.sx, sm.su, par, tid, NT, sync);
     }
@@ -1091,7 +1099,8 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
   // the cooperative kernel wins for the quadrupeds and H1 at any batch size (H1 x4096: 6.0 vs 6.5 ms, r02) and for
   // every robot when the batch is too small to fill the GPU with one warp per trial point (single-instance latency)
   // MPXB_WB_TRIAL=1: warp form only; =2: cooperative form for every class and batch size (measurement switches)
-  const bool coop_ok = legacy != 1 && h.tree_ok && h.nbody <= NB && (legacy == 2 || NV <= MPXB_INV_MAXNV || io.E * (io.N + 1) <= 148 * 8);
+  const bool coop_ok = legacy != 1 && h.tree_ok && h.nbody <= NB && (NV > MPXB_INV_MAXNV || h.contact_solve) &&
+                       (legacy == 2 || NV <= MPXB_INV_MAXNV || io.E * (io.N + 1) <= 148 * 8);
   TrialOut to = to_in;
   // first pass / eager evaluation: cooperative (if available) resp. warp-per-trial; second pass: both, selected on the
   // device by the number of environments that still need the smaller steps
@@ -1114,9 +1123,10 @@ inline int wb_class_trial(const WbModel& h, const WbModel* dev, const ModelIO& i
   }
   if (run_coop) {
     to.sel = second ? 1 : 0;
-    // one warp per item for the quadrupeds (no CTA barrier, 14 items resident per SM: Go2 x1024 0.71 -> 0.59 ms, r02w);
-    // H1 keeps two warps (6.45 vs 6.75 ms at x4096).  MPXB_TRIAL_NT=32 / 64 forces a form (measurement switch)
-    static const int nt32 = [] { const char* v = getenv("MPXB_TRIAL_NT"); return (v && v[0] == '3') ? 1 : ((v && v[0] == '6') ? 0 : (NV <= 18 ? 1 : 0)); }();
+    // one warp per item for the quadrupeds and H1 (no CTA barrier; 16 resp. 12 items resident per SM once the item's
+    // shared memory carries neither L^-1 nor the acceleration problems): Go2 x1024 0.71 -> 0.41 ms, H1 x4096 5.24 ->
+    // 4.87 ms (r02y).  MPXB_TRIAL_NT=32 / 64 forces a form (measurement switch)
+    static const int nt32 = [] { const char* v = getenv("MPXB_TRIAL_NT"); return (v && v[0] == '3') ? 1 : ((v && v[0] == '6') ? 0 : (NV <= MPXB_INV_MAXNV ? 1 : 0)); }();
     using S = WbTrialSmem<NB, NV, NC>;
     const int items = io.E * to.nia * (io.N + 1);
     const int grid = (second && items > 148 * 32) ? 148 * 32 : items;

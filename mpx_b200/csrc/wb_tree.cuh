@@ -28,7 +28,9 @@ template <int NB, int NV, int NC, int NI> struct WbTree {
   float pos[NB][3], quat[NB][4];
   float S[NV][6], U[NV][6], rv[NV][6];
   float v[NB][6], c[NB][6], I[NB][10], Ic[NB][10], h[NB][6], Fb[NB][6];
-  float al[3][NB][6], F[3][NB][6];
+  // acceleration problems of the linearise kernel only: trial / interface instantiations (NI == 1) carry no items
+  // and drop them (3 KB of an H1 trial item's 22 KB)
+  float al[NI > 1 ? 3 : 1][NI > 1 ? NB : 1][6], F[NI > 1 ? 3 : 1][NI > 1 ? NB : 1][6];
   float rc[NC][3];  // foot position relative to the reference point (base position)
   float wq[4][3];   // world angular rate of a unit perturbation of each raw base-quaternion component
   float vt[6], cg[6];
