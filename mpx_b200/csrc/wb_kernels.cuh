@@ -529,11 +529,13 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 //   S6  (direction, body) force perturbations + subtree sums
 //   S7  thread d: folded tangents of direction d (analytic) -> column d of [A | B] (wb_s3_tangent), A'V / B'V
 //   P5  cost gradient, q, r, Gauss-Newton blocks
-// resident CTAs per SM the register allocation is tuned for (measured on B200, Go2 x1024: 6 CTAs of 64 threads at
-// 168 registers beat both 4 at 255 and 8 at 128; H1 x4096: 4 CTAs of 128 threads at 128 registers -- 16 warps per SM,
+// resident knots per SM the register allocation is tuned for.  Quadrupeds: 8 knots of 64 threads at 128 registers (16
+// warps per SM) since the per-knot shared memory is 26.6 KB (narrow folded-tangent block over the tree's scratch
+// block); at 36 KB per knot 6 knots at 168 registers were the best shared memory allowed (Go2 x1024: 1.76 -> 1.4 ms).
+// H1 x4096: 4 CTAs of 128 threads at 128 registers -- 16 warps per SM,
 // no spills -- 11.5 ms vs 12.3 ms for 4 x 96 threads at 168 and 14.7 ms for 3 x 128 at 168, r02y)
 #ifndef MPXB_LIN3_MINB
-#define MPXB_LIN3_MINB (NT <= 64 ? 6 : (NT <= 96 ? 4 : (NV <= 25 ? 4 : 2)))
+#define MPXB_LIN3_MINB (NT <= 64 ? 8 : (NT <= 96 ? 4 : (NV <= 25 ? 4 : 2)))
 #endif
 // knots per CTA: the kernel is ~16 k SASS instructions of straight-line code that every CTA executes once, and
 // instruction fetch is 15 % of its stall samples; KPB > 1 puts KPB knots -- NT threads, one shared-memory struct and one
@@ -554,10 +556,15 @@ template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   // tr | fold | dw are dead once the columns of [A | B] are out: the weight matrix W is staged over them for the
   // Gauss-Newton / cost stage (its reads would otherwise go to L2: 216 KB of shared memory leave ~40 KB of L1)
   alignas(16) WbTree<NB, NV, NC, NI> tr;
-  // folded tangents t1 | t2 | e | h | dfeet of every x-direction ([row][direction], wb_tree_fold_coop) + direction frames
-  static constexpr int FW = 2 * NV + 1;
-  float fold[(3 * NV + 2 * NF) * FW];
-  WbDirW<NV> dw[NV + 1];
+  // folded tangents of every x-direction (wb_tree_fold_coop): t1 for all nq + nv directions ([row][direction]); the
+  // rows t2 | e | h | dfeet exist for the nq position directions only (+ one all-zero column).  That narrow block lives
+  // over the tree's scratch block when it fits (the quadrupeds: 36 -> 27 KB per knot, 8 knots per SM instead of 6)
+  static constexpr int FW = 2 * NV + 1, FWN = NV + 2, NROWN = 2 * NV + 2 * NF;
+  static constexpr bool FOLDN_OVER_TREE = NROWN * FWN <= WbTree<NB, NV, NC, NI>::SCRATCH;
+  float fold[NV * FW];
+  float foldn_own[FOLDN_OVER_TREE ? 4 : NROWN * FWN];
+  WbDirW<NV> dw[NV - 2];   // direction frames of the 4 + nj position directions that move a subtree
+  __device__ float* foldn() { return FOLDN_OVER_TREE ? tr.scratch() : foldn_own; }
 };
 
 __device__ __forceinline__ void wb_cp_async16(float* dst, const float* src) {
@@ -664,8 +671,9 @@ __global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
     float* B = o.B + (size_t(e) * N + t) * n * o.ldB;
     // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
     // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
-    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, tid, NT, sync,
-                      reinterpret_cast<const WbFoldTable*>(mdp + 1));
+    float* const foldn = sm.foldn();
+    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, foldn, S::FWN,
+                      tid, NT, sync, reinterpret_cast<const WbFoldTable*>(mdp + 1));
     sync();
     if (tid < NDS + m) {
       constexpr int FW = S::FW, NF3 = 3 * NC;
@@ -676,8 +684,13 @@ __global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
 #pragma unroll
         for (int i = 0; i < NV; ++i) t1[i] = sm.fold[i * FW + cc];
       }
-      const WbStrided t2{sm.fold + NV * FW + cc, FW}, ee{sm.fold + 2 * NV * FW + cc, FW}, hh{sm.fold + 3 * NV * FW + cc, FW},
-          dfeet{sm.fold + (3 * NV + NF3) * FW + cc, FW};
+      // a velocity direction has t2 = t1 and e = h = dfeet = 0 (the zero column NQ of the narrow block)
+      constexpr int FWN = S::FWN;
+      const bool posdir = !is_u && cc < NQ;
+      const int cn = posdir ? cc : NQ;
+      const WbStrided t2 = posdir ? WbStrided{foldn + cc, FWN} : WbStrided{sm.fold + cc, FW};
+      const WbStrided ee{foldn + NV * FWN + cn, FWN}, hh{foldn + 2 * NV * FWN + cn, FWN},
+          dfeet{foldn + (2 * NV + NF3) * FWN + cn, FWN};
       float atv = 0.f;
       float* dst = is_u ? B + (tid - NDS) : A + tid;
       const int ld = is_u ? o.ldB : o.ldA;

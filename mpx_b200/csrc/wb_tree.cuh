@@ -25,16 +25,21 @@
 namespace mpxb {
 
 template <int NB, int NV, int NC, int NI> struct WbTree {
+  // ---- scratch block: nothing from here to `F` is read once the direction frames exist (wb_tree_fold_coop, F1), so
+  // the linearise kernel lets the narrow half of the folded tangents live over it (scratch() / SCRATCH floats)
   float pos[NB][3], quat[NB][4];
-  float S[NV][6], U[NV][6], rv[NV][6];
   float v[NB][6], c[NB][6], I[NB][10], Ic[NB][10], h[NB][6], Fb[NB][6];
   // acceleration problems of the linearise kernel only: trial / interface instantiations (NI == 1) carry no items
   // and drop them (3 KB of an H1 trial item's 22 KB)
   float al[NI > 1 ? 3 : 1][NI > 1 ? NB : 1][6], F[NI > 1 ? 3 : 1][NI > 1 ? NB : 1][6];
+  // ---- live until the columns of [A | B] are out
+  float S[NV][6], U[NV][6], rv[NV][6];
   float rc[NC][3];  // foot position relative to the reference point (base position)
   float wq[4][3];   // world angular rate of a unit perturbation of each raw base-quaternion component
   float vt[6], cg[6];
   float g[NI][6];
+  static constexpr int SCRATCH = NB * (3 + 4 + 6 + 6 + 10 + 10 + 6 + 6) + 2 * (NI > 1 ? 3 : 1) * (NI > 1 ? NB : 1) * 6;
+  HD float* scratch() { return &pos[0][0]; }
 };
 
 template <class A, class B> HD float dot6(const A* a, const B* b) {
@@ -418,8 +423,11 @@ HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const 
 // work items instead of one long thread per direction (which kept 19 of 64 lanes busy).
 //   F1  worker per position direction: its frame (S_d, the four X vectors, the three mu, moves / ancestor masks)
 //   F2  items (direction, dof)  -> t1, t2, e   and items (direction, foot) -> h, dfeet
-// Results go to `fold` ([row][col], row = t1 NV | t2 NV | e NV | h 3NC | dfeet 3NC, ld = FW >= nq + nv), from where
-// the column threads of the tangent stage pick them up.
+// Results go to `fold` ([row][col], rows t1 NV, ld = FW >= nq + nv, all x-directions) and to the NARROW block `foldn`
+// ([row][col], rows t2 NV | e NV | h 3NC | dfeet 3NC, ld = FWN >= nq + 1, position directions only: for a velocity
+// direction t2 = t1 and e = h = dfeet = 0, which the readers take from t1 and from the all-zero column nq of foldn),
+// from where the column threads of the tangent stage pick them up.  F1 is the last reader of the tree's scratch
+// block, so foldn may live over it.
 template <int NV> struct WbDirW {
   float Sd[6], X[4][6], mu[3][6];
   uint32_t moves, anc;
@@ -428,14 +436,14 @@ template <int NV> struct WbDirW {
 template <int NB, int NV, int NC, int NI, class Sync>
 HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const float* J, const float* w,
                           const float* a, const float* z, const float* y, const float* grf, const float* wvz,
-                          WbDirW<NV>* dw, float* fold, int FW, int lane, int nl, Sync sync,
+                          WbDirW<NV>* dw, float* fold, int FW, float* foldn, int FWN, int lane, int nl, Sync sync,
                           const WbFoldTable* ft = nullptr) {
   constexpr int NF = 3 * NC, NQ = NV + 1;
   constexpr int npos = 4 + NV - 6, ncol = NQ + NV;
   // F1
   for (int col = 3 + lane; col < NQ; col += nl) {
     const int D = col - 3;
-    WbDirW<NV>& d = dw[col];
+    WbDirW<NV>& d = dw[col - 3];
     const int b0 = md.dir_b0[D], nbd = md.dir_nb[D], off = md.dir_off[D];
     const bool isq = D < 4;
     float Sd[6];
@@ -467,6 +475,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
   sync();
   // F2
   const int nitem1 = ncol * NV, nitem2 = ncol * NC;
+  for (int r = lane; r < 2 * NV + 2 * NF; r += nl) foldn[r * FWN + NQ] = 0.f;   // the zero column
   if (ft) {
     // table-driven (col, dof) items: the segments are multiples of 32 items, so a warp runs one branch
     const int end_mv = ft->end_mv, end_anc = ft->end_anc, end_vel = ft->end_vel, end_zero = ft->end_zero;
@@ -476,7 +485,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
       const int col = int(ent >> 5), i = int(ent & 31u);
       float t1 = 0.f, t2 = 0.f, e = 0.f;
       if (it < end_anc) {
-        const WbDirW<NV>& d = dw[col];
+        const WbDirW<NV>& d = dw[col - 3];
         const bool mv = it < end_mv;
         if (mv) {
           const float dD = dot6(tr.S[i], tr.g[d.off + md.dof_body[i] - d.b0]);
@@ -513,8 +522,10 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
         t1 = -s; t2 = -s;
       }
       fold[i * FW + col] = t1;
-      fold[(NV + i) * FW + col] = t2;
-      fold[(2 * NV + i) * FW + col] = e;
+      if (col < NQ) {
+        foldn[i * FWN + col] = t2;
+        foldn[(NV + i) * FWN + col] = e;
+      }
     }
   }
   for (int it = (ft ? nitem1 + lane : lane); it < nitem1 + nitem2; it += nl) {
@@ -529,7 +540,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
         else if ((md.dof_anc[D - npos] >> i) & 1u) s = dot6(tr.S[i], tr.g[off]);
         t1 = -s; t2 = -s;
       } else if (col >= 3) {
-        const WbDirW<NV>& d = dw[col];
+        const WbDirW<NV>& d = dw[col - 3];
         const bool mv = (d.moves >> i) & 1u;
         if (mv) {
           const float dD = dot6(tr.S[i], tr.g[d.off + md.dof_body[i] - d.b0]);
@@ -561,8 +572,10 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
         }
       }
       fold[i * FW + col] = t1;
-      fold[(NV + i) * FW + col] = t2;
-      fold[(2 * NV + i) * FW + col] = e;
+      if (col < NQ) {
+        foldn[i * FWN + col] = t2;
+        foldn[(NV + i) * FWN + col] = e;
+      }
     } else {
       const int it2 = it - nitem1;
       const int col = it2 / NC, c = it2 - col * NC;
@@ -570,7 +583,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
       if (col < 3) {
         df[col] = 1.f;
       } else if (col < NQ) {
-        const WbDirW<NV>& d = dw[col];
+        const WbDirW<NV>& d = dw[col - 3];
         const int bc = md.contact_body[c];
         if (bc >= d.b0 && bc < d.b0 + d.nbd) {
           float pc[3];
@@ -586,10 +599,11 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
           }
         }
       }
-      for (int k = 0; k < 3; ++k) {
-        fold[(3 * NV + 3 * c + k) * FW + col] = hc[k];
-        fold[(3 * NV + NF + 3 * c + k) * FW + col] = df[k];
-      }
+      if (col < NQ)
+        for (int k = 0; k < 3; ++k) {
+          foldn[(2 * NV + 3 * c + k) * FWN + col] = hc[k];
+          foldn[(2 * NV + NF + 3 * c + k) * FWN + col] = df[k];
+        }
     }
   }
 }

@@ -99,26 +99,37 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
   wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
   wb_tree_items(md, tr, 0, 1, nosync);
-  constexpr int NF = 3 * NC, FW = 2 * NV + 1;
+  constexpr int NF = 3 * NC, FW = 2 * NV + 1, FWN = NV + 2, NROWN = 2 * NV + 2 * NF;
   static WbDirW<NV> dw[NV + 1];
-  static float fold[(3 * NV + 2 * NF) * FW];
-  // the device runs the table-driven item order (wb_build_fold_table); both enumerations must fill `fold` identically
+  // t1 of every x-direction in `fold`; t2 | e | h | dfeet of the position directions (+ the zero column nq) in the narrow
+  // block `foldn` -- placed over the tree's scratch block when it fits, exactly as the linearise kernel does, so the
+  // host run also proves that nothing reads the scratch block after the direction frames are built
+  static float fold[NV * FW], fold_plain[NV * FW], foldn_own[NROWN * FWN], foldn_plain[NROWN * FWN];
+  constexpr bool over_tree = NROWN * FWN <= WbTree<NB, NV, NC, NI>::SCRATCH;
+  float* foldn = over_tree ? tr.scratch() : foldn_own;
+  // the device runs the table-driven item order (wb_build_fold_table); both enumerations must fill the blocks identically
   static WbFoldTable ft;
   wb_build_fold_table(md, &ft);
-  static float fold_plain[(3 * NV + 2 * NF) * FW];
-  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold_plain, FW, 0, 1, nosync);
-  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, 0, 1, nosync, &ft);
-  for (int r = 0; r < 3 * NV + 2 * NF; ++r)
+  static WbTree<NB, NV, NC, NI> tr_copy;
+  tr_copy = tr;
+  wb_tree_fold_coop(md, tr_copy, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold_plain, FW, foldn_plain, FWN, 0, 1, nosync);
+  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, foldn, FWN, 0, 1, nosync, &ft);
+  for (int r = 0; r < NV; ++r)
     for (int c2 = 0; c2 < nq + nv; ++c2)
       if (!(fold[r * FW + c2] == fold_plain[r * FW + c2])) return -100;
+  for (int r = 0; r < NROWN; ++r)
+    for (int c2 = 0; c2 <= nq; ++c2)
+      if (!(foldn[r * FWN + c2] == foldn_plain[r * FWN + c2])) return -101;
   std::vector<float> col(n);
   for (int d = 0; d < nq + nv + m; ++d) {
     float t1[NV] = {0};
     const int is_u = d >= nq + nv;
     const int cc = is_u ? 0 : d;
     if (!is_u) for (int i = 0; i < NV; ++i) t1[i] = fold[i * FW + d];
-    const WbStrided t2{fold + NV * FW + cc, FW}, e{fold + 2 * NV * FW + cc, FW}, h{fold + 3 * NV * FW + cc, FW},
-        dfeet{fold + (3 * NV + NF) * FW + cc, FW};
+    const bool posdir = !is_u && cc < nq;
+    const int cn = posdir ? cc : nq;
+    const WbStrided t2 = posdir ? WbStrided{foldn + cc, FWN} : WbStrided{fold + cc, FW};
+    const WbStrided e{foldn + NV * FWN + cn, FWN}, h{foldn + 2 * NV * FWN + cn, FWN}, dfeet{foldn + (2 * NV + NF) * FWN + cn, FWN};
     float* cp = col.data();
     if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
