@@ -534,8 +534,11 @@ __global__ void __launch_bounds__(NT) wb_linearize_kernel(const WbModel* __restr
 // block); at 36 KB per knot 6 knots at 168 registers were the best shared memory allowed (Go2 x1024: 1.76 -> 1.4 ms).
 // H1 x4096: 4 CTAs of 128 threads at 128 registers -- 16 warps per SM,
 // no spills -- 11.5 ms vs 12.3 ms for 4 x 96 threads at 168 and 14.7 ms for 3 x 128 at 168, r02y)
+#ifndef MPXB_LIN3_MINB_H1
+#define MPXB_LIN3_MINB_H1 4
+#endif
 #ifndef MPXB_LIN3_MINB
-#define MPXB_LIN3_MINB (NT <= 64 ? 8 : (NT <= 96 ? 4 : (NV <= 25 ? 4 : 2)))
+#define MPXB_LIN3_MINB (NT <= 64 ? 8 : (NT <= 96 ? 4 : (NV <= 25 ? MPXB_LIN3_MINB_H1 : 2)))
 #endif
 // knots per CTA: the kernel is ~16 k SASS instructions of straight-line code that every CTA executes once, and
 // instruction fetch is 15 % of its stall samples; KPB > 1 puts KPB knots -- NT threads, one shared-memory struct and one
@@ -559,12 +562,15 @@ template <int NB, int NV, int NC, int NI, int NT> struct WbLin3Smem {
   // folded tangents of every x-direction (wb_tree_fold_coop): t1 for all nq + nv directions ([row][direction]); the
   // rows t2 | e | h | dfeet exist for the nq position directions only (+ one all-zero column).  That narrow block lives
   // over the tree's scratch block when it fits (the quadrupeds: 36 -> 27 KB per knot, 8 knots per SM instead of 6)
-  static constexpr int FW = 2 * NV + 1, FWN = NV + 2, NROWN = 2 * NV + 2 * NF;
-  static constexpr bool FOLDN_OVER_TREE = NROWN * FWN <= WbTree<NB, NV, NC, NI>::SCRATCH;
+  static constexpr int FW = 2 * NV + 1, FWN = NV + 2, SZN = 2 * NV * FWN, SZH = 2 * NF * FWN;
+  // first fit over the scratch block: t2 | e (quadrupeds, H1), then h | dfeet behind them (quadrupeds)
+  static constexpr int SCR = WbTree<NB, NV, NC, NI>::SCRATCH;
+  static constexpr bool N_OVER_TREE = SZN <= SCR, H_OVER_TREE = N_OVER_TREE && SZN + SZH <= SCR;
   float fold[NV * FW];
-  float foldn_own[FOLDN_OVER_TREE ? 4 : NROWN * FWN];
+  float foldn_own[N_OVER_TREE ? 4 : SZN], foldh_own[H_OVER_TREE ? 4 : SZH];
   WbDirW<NV> dw[NV - 2];   // direction frames of the 4 + nj position directions that move a subtree
-  __device__ float* foldn() { return FOLDN_OVER_TREE ? tr.scratch() : foldn_own; }
+  __device__ float* foldn() { return N_OVER_TREE ? tr.scratch() : foldn_own; }
+  __device__ float* foldh() { return H_OVER_TREE ? tr.scratch() + SZN : foldh_own; }
 };
 
 __device__ __forceinline__ void wb_cp_async16(float* dst, const float* src) {
@@ -672,8 +678,9 @@ __global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
     // S7: folded tangents of all directions as cooperative work items, then thread d -> column d of [A | B].  The
     // Gauss-Newton blocks follow without a barrier, so the warps that hold few columns start on them early.
     float* const foldn = sm.foldn();
-    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, foldn, S::FWN,
-                      tid, NT, sync, reinterpret_cast<const WbFoldTable*>(mdp + 1));
+    float* const foldh = sm.foldh();
+    wb_tree_fold_coop(md, sm.tr, sm.k.J, sm.k.w, sm.k.a, sm.k.z, sm.k.y, sm.k.grf, sm.k.wvz, sm.dw, sm.fold, S::FW, foldn, foldh,
+                      S::FWN, tid, NT, sync, reinterpret_cast<const WbFoldTable*>(mdp + 1));
     sync();
     if (tid < NDS + m) {
       constexpr int FW = S::FW, NF3 = 3 * NC;
@@ -689,8 +696,7 @@ __global__ void __launch_bounds__(NT * KPB, (MPXB_LIN3_MINB + KPB - 1) / KPB)
       const bool posdir = !is_u && cc < NQ;
       const int cn = posdir ? cc : NQ;
       const WbStrided t2 = posdir ? WbStrided{foldn + cc, FWN} : WbStrided{sm.fold + cc, FW};
-      const WbStrided ee{foldn + NV * FWN + cn, FWN}, hh{foldn + 2 * NV * FWN + cn, FWN},
-          dfeet{foldn + (2 * NV + NF3) * FWN + cn, FWN};
+      const WbStrided ee{foldn + NV * FWN + cn, FWN}, hh{foldh + cn, FWN}, dfeet{foldh + NF3 * FWN + cn, FWN};
       float atv = 0.f;
       float* dst = is_u ? B + (tid - NDS) : A + tid;
       const int ld = is_u ? o.ldB : o.ldA;

@@ -423,11 +423,11 @@ HD void wb_tree_fold(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const 
 // work items instead of one long thread per direction (which kept 19 of 64 lanes busy).
 //   F1  worker per position direction: its frame (S_d, the four X vectors, the three mu, moves / ancestor masks)
 //   F2  items (direction, dof)  -> t1, t2, e   and items (direction, foot) -> h, dfeet
-// Results go to `fold` ([row][col], rows t1 NV, ld = FW >= nq + nv, all x-directions) and to the NARROW block `foldn`
-// ([row][col], rows t2 NV | e NV | h 3NC | dfeet 3NC, ld = FWN >= nq + 1, position directions only: for a velocity
-// direction t2 = t1 and e = h = dfeet = 0, which the readers take from t1 and from the all-zero column nq of foldn),
-// from where the column threads of the tangent stage pick them up.  F1 is the last reader of the tree's scratch
-// block, so foldn may live over it.
+// Results go to `fold` ([row][col], rows t1 NV, ld = FW >= nq + nv, all x-directions) and to the NARROW blocks `foldn`
+// (rows t2 NV | e NV) and `foldh` (rows h 3NC | dfeet 3NC), both [row][col] with ld = FWN >= nq + 1, position
+// directions only: for a velocity direction t2 = t1 and e = h = dfeet = 0, which the readers take from t1 and from the
+// all-zero column nq of the narrow blocks; from there the column threads of the tangent stage pick them up.  F1 is the
+// last reader of the tree's scratch block, so the narrow blocks may live over it.
 template <int NV> struct WbDirW {
   float Sd[6], X[4][6], mu[3][6];
   uint32_t moves, anc;
@@ -436,7 +436,7 @@ template <int NV> struct WbDirW {
 template <int NB, int NV, int NC, int NI, class Sync>
 HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, const float* J, const float* w,
                           const float* a, const float* z, const float* y, const float* grf, const float* wvz,
-                          WbDirW<NV>* dw, float* fold, int FW, float* foldn, int FWN, int lane, int nl, Sync sync,
+                          WbDirW<NV>* dw, float* fold, int FW, float* foldn, float* foldh, int FWN, int lane, int nl, Sync sync,
                           const WbFoldTable* ft = nullptr) {
   constexpr int NF = 3 * NC, NQ = NV + 1;
   constexpr int npos = 4 + NV - 6, ncol = NQ + NV;
@@ -475,7 +475,7 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
   sync();
   // F2
   const int nitem1 = ncol * NV, nitem2 = ncol * NC;
-  for (int r = lane; r < 2 * NV + 2 * NF; r += nl) foldn[r * FWN + NQ] = 0.f;   // the zero column
+  for (int r = lane; r < 2 * NV + 2 * NF; r += nl) (r < 2 * NV ? foldn + r * FWN : foldh + (r - 2 * NV) * FWN)[NQ] = 0.f;   // the zero columns
   if (ft) {
     // table-driven (col, dof) items: the segments are multiples of 32 items, so a warp runs one branch
     const int end_mv = ft->end_mv, end_anc = ft->end_anc, end_vel = ft->end_vel, end_zero = ft->end_zero;
@@ -601,8 +601,8 @@ HD void wb_tree_fold_coop(const WbModel& md, const WbTree<NB, NV, NC, NI>& tr, c
       }
       if (col < NQ)
         for (int k = 0; k < 3; ++k) {
-          foldn[(2 * NV + 3 * c + k) * FWN + col] = hc[k];
-          foldn[(2 * NV + NF + 3 * c + k) * FWN + col] = df[k];
+          foldh[(3 * c + k) * FWN + col] = hc[k];
+          foldh[(NF + 3 * c + k) * FWN + col] = df[k];
         }
     }
   }

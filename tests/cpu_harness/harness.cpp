@@ -99,27 +99,32 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
   for (int i = 0; i < n; ++i) xn[i] = k.xn[i];
   wb_tree_acc(md, tr, k.w, k.a, k.z, 0, 1, nosync);
   wb_tree_items(md, tr, 0, 1, nosync);
-  constexpr int NF = 3 * NC, FW = 2 * NV + 1, FWN = NV + 2, NROWN = 2 * NV + 2 * NF;
+  constexpr int NF = 3 * NC, FW = 2 * NV + 1, FWN = NV + 2, SZN = 2 * NV * FWN, SZH = 2 * NF * FWN;
   static WbDirW<NV> dw[NV + 1];
-  // t1 of every x-direction in `fold`; t2 | e | h | dfeet of the position directions (+ the zero column nq) in the narrow
-  // block `foldn` -- placed over the tree's scratch block when it fits, exactly as the linearise kernel does, so the
-  // host run also proves that nothing reads the scratch block after the direction frames are built
-  static float fold[NV * FW], fold_plain[NV * FW], foldn_own[NROWN * FWN], foldn_plain[NROWN * FWN];
-  constexpr bool over_tree = NROWN * FWN <= WbTree<NB, NV, NC, NI>::SCRATCH;
-  float* foldn = over_tree ? tr.scratch() : foldn_own;
+  // t1 of every x-direction in `fold`; t2 | e (foldn) and h | dfeet (foldh) of the position directions (+ the zero column
+  // nq) in the narrow blocks -- placed over the tree's scratch block where they fit, exactly as the linearise kernel
+  // does, so the host run also proves that nothing reads the scratch block after the direction frames are built
+  static float fold[NV * FW], fold_plain[NV * FW], foldn_own[SZN], foldh_own[SZH], foldn_plain[SZN], foldh_plain[SZH];
+  constexpr int SCR = WbTree<NB, NV, NC, NI>::SCRATCH;
+  constexpr bool n_over = SZN <= SCR, h_over = n_over && SZN + SZH <= SCR;
+  float* foldn = n_over ? tr.scratch() : foldn_own;
+  float* foldh = h_over ? tr.scratch() + SZN : foldh_own;
   // the device runs the table-driven item order (wb_build_fold_table); both enumerations must fill the blocks identically
   static WbFoldTable ft;
   wb_build_fold_table(md, &ft);
   static WbTree<NB, NV, NC, NI> tr_copy;
   tr_copy = tr;
-  wb_tree_fold_coop(md, tr_copy, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold_plain, FW, foldn_plain, FWN, 0, 1, nosync);
-  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, foldn, FWN, 0, 1, nosync, &ft);
+  wb_tree_fold_coop(md, tr_copy, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold_plain, FW, foldn_plain, foldh_plain, FWN, 0, 1, nosync);
+  wb_tree_fold_coop(md, tr, k.J, k.w, k.a, k.z, k.y, k.grf, k.wvz, dw, fold, FW, foldn, foldh, FWN, 0, 1, nosync, &ft);
   for (int r = 0; r < NV; ++r)
     for (int c2 = 0; c2 < nq + nv; ++c2)
       if (!(fold[r * FW + c2] == fold_plain[r * FW + c2])) return -100;
-  for (int r = 0; r < NROWN; ++r)
-    for (int c2 = 0; c2 <= nq; ++c2)
+  for (int c2 = 0; c2 <= nq; ++c2) {
+    for (int r = 0; r < 2 * NV; ++r)
       if (!(foldn[r * FWN + c2] == foldn_plain[r * FWN + c2])) return -101;
+    for (int r = 0; r < 2 * NF; ++r)
+      if (!(foldh[r * FWN + c2] == foldh_plain[r * FWN + c2])) return -102;
+  }
   std::vector<float> col(n);
   for (int d = 0; d < nq + nv + m; ++d) {
     float t1[NV] = {0};
@@ -129,7 +134,7 @@ int tree_t(const WbModel& md, const float* x, const float* u, const float* conta
     const bool posdir = !is_u && cc < nq;
     const int cn = posdir ? cc : nq;
     const WbStrided t2 = posdir ? WbStrided{foldn + cc, FWN} : WbStrided{fold + cc, FW};
-    const WbStrided e{foldn + NV * FWN + cn, FWN}, h{foldn + 2 * NV * FWN + cn, FWN}, dfeet{foldn + (2 * NV + NF) * FWN + cn, FWN};
+    const WbStrided e{foldn + NV * FWN + cn, FWN}, h{foldh + cn, FWN}, dfeet{foldh + NF * FWN + cn, FWN};
     float* cp = col.data();
     if constexpr (NV <= MPXB_INV_MAXNV) wb_s3_tangent_inv<NV, NC>(md, k, contact, is_u, is_u ? d - nq - nv : d, t1, t2, e, h, dfeet,
                           [cp](int i, float v) { cp[i] = v; });
