@@ -81,7 +81,9 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
             if (k < 3) cv[k] = cv[k] + Rb[3 * k + a] * qvel[3 + a];
             ca[k] = ca[k] + cd[a][k] * qvel[3 + a];
           }
-        // world angular rate of d quat_raw[k]: 2 vec(d qhat * conj(qhat))
+        // world angular rate of d quat_raw[k]: 2 vec(d qhat * conj(qhat)) -- derivative data, like rv below: the
+        // trial / interface instantiations (NI == 1) skip both
+        if constexpr (NI > 1)
         for (int k = 0; k < 4; ++k) {
           Dual q4[4], qn[4];
           for (int i = 0; i < 4; ++i) q4[i] = Dual(qpos[3 + i], i == k ? 1.f : 0.f);
@@ -118,7 +120,7 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
           const float qd = qvel[dj];
           for (int k = 0; k < 6; ++k) {
             tr.S[dj][k] = cdof[k];
-            tr.rv[dj][k] = cv[k] + (cv[k] + cdof[k] * qd);
+            if constexpr (NI > 1) tr.rv[dj][k] = cv[k] + (cv[k] + cdof[k] * qd);
             ca[k] = ca[k] + cd[k] * qd;
             cv[k] = cv[k] + cdof[k] * qd;
           }
@@ -127,7 +129,7 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
       for (int i = 0; i < 3; ++i) tr.pos[b][i] = pos[i];
       for (int i = 0; i < 4; ++i) tr.quat[b][i] = quat[i];
       for (int i = 0; i < 6; ++i) { tr.v[b][i] = cv[i]; tr.c[b][i] = ca[i]; }
-      if (lvl == 0)
+      if (NI > 1 && lvl == 0)
         for (int k = 0; k < 6; ++k) {
           for (int a = 0; a < 3; ++a) tr.rv[a][k] = 0.f;
           for (int a = 3; a < 6; ++a) tr.rv[a][k] = cv[k] + vt0[k];  // own copy: the other leaf workers write tr.vt too
