@@ -67,6 +67,26 @@ def test_random_lq(n, m, T, lq_mode):
         assert torch.equal(g[0], g[1])
 
 
+def test_small_system_kernel_and_its_fallbacks():
+    """Sequential LQ of the SRBD size: the whole-horizon-in-shared-memory kernel (csrc/lq_small.cuh) serves horizons up
+    to N = 47 and batches up to 6 waves of CTAs, the streaming kernel (csrc/lq.cuh) everything else.  Every route must
+    meet the oracle, and a batch must not depend on which route its size selects beyond rounding."""
+    from mpx_b200 import _lib
+    from mpx_b200.primal_dual_ilqr.optimizers import tvlqr_solve
+    for T, E in [(1, 1), (25, 3), (47, 2), (48, 2), (90, 1)]:      # 47 is the last horizon that fits, 48 streams
+        prob = random_lq(13, 12, T, seed=100 + T)
+        got = tvlqr_solve(*_to_gpu(prob, E), lq_mode=_lib.LQ_SEQUENTIAL)
+        _check(got, _oracle(prob, False), 2e-4)
+        for g in got:
+            assert torch.equal(g[0], g[E - 1])
+    prob = random_lq(13, 12, 25, seed=7)
+    small = tvlqr_solve(*_to_gpu(prob, 4), lq_mode=_lib.LQ_SEQUENTIAL)         # lq_small
+    large = tvlqr_solve(*_to_gpu(prob, 6 * 148 + 1), lq_mode=_lib.LQ_SEQUENTIAL)   # streaming kernel
+    _check(large, _oracle(prob, False), 2e-4)
+    for a, b in zip(small, large):
+        assert torch.allclose(a[0], b[0], rtol=2e-4, atol=2e-4 * float(a[0].abs().max()))
+
+
 def test_parallel_scan_long_horizon_and_odd_lengths():
     """Hillis-Steele levels with N + 1 not a power of two, and a long horizon (Talos sizes, N = 200)."""
     from mpx_b200 import _lib
