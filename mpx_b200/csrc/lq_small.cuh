@@ -4,7 +4,8 @@
 // every result K_t, k_t, P_t, p_t, dX, dU -- lives in the shared memory of one CTA (127 KB for SRBD at N = 25), so
 // the time loop touches no global memory at all: one coalesced load phase with every request in flight at once, 4 block
 // barriers per knot, one coalesced store phase.  The general kernel (lq.cuh) streams each knot through cp.async and
-// spends 8.9 us per knot on a 13 x 13 problem; this one spends ~1 us (E = 1 SRBD: LQ 222 -> 30 us).
+// spends 8.9 us per knot on a 13 x 13 problem; this one spends 2.9 us (E = 1 SRBD: LQ 223 -> 72 us, r02w), 40 % of it
+// at the barrier behind the per-column factorisation + solve, the serial chain of the knot.
 //
 // Per knot (the reference recursion, dense general form):
 //   S1   PA = P+ A,  PB = P+ B,  w = p+ + P+ c
