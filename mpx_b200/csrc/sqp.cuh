@@ -235,22 +235,24 @@ __global__ void shift_extract_kernel(int E, int N, int n, int m, int nj, int shi
     }
   }
   __syncthreads();
+  // (32-bit indices, no division by the runtime row length: the flat size_t form spent most of the kernel in 64-bit
+  // divide sequences)
+  const int nxi = (N + 1) * n, nui = N * m, nt = int(blockDim.x);
   if (nan) {
-    for (size_t i = tid; i < nx; i += blockDim.x) { X0e[i] = x0[size_t(e) * n + (i % n)]; V0e[i] = 0.f; }
-    for (size_t i = tid; i < nu; i += blockDim.x) U0e[i] = u_ref[i % m];
+    for (int t = 0; t <= N; ++t)
+      for (int j = tid; j < n; j += nt) { X0e[t * n + j] = x0[size_t(e) * n + j]; V0e[t * n + j] = 0.f; }
+    for (int t = 0; t < N; ++t)
+      for (int j = tid; j < m; j += nt) U0e[t * m + j] = u_ref[j];
     return;
   }
-  for (size_t i = tid; i < nx; i += blockDim.x) {
-    const int t = int(i / n), j = int(i % n);
-    const int ts = min(t + shift, N);
-    X0e[i] = Xe[size_t(ts) * n + j];
-    V0e[i] = Ve[size_t(ts) * n + j];
-  }
-  for (size_t i = tid; i < nu; i += blockDim.x) {
-    const int t = int(i / m), j = int(i % m);
-    const int ts = min(t + shift, N - 1);
-    U0e[i] = Ue[size_t(ts) * m + j];
-  }
+  // rows t <= N - shift are one contiguous block moved down by `shift` rows; the rows behind repeat the last knot
+  const int sx = shift * n, su = shift * m;
+  for (int i = tid; i < nxi - sx; i += nt) { X0e[i] = Xe[i + sx]; V0e[i] = Ve[i + sx]; }
+  for (int t = max(N + 1 - shift, 0); t <= N; ++t)
+    for (int j = tid; j < n; j += nt) { X0e[t * n + j] = Xe[N * n + j]; V0e[t * n + j] = Ve[N * n + j]; }
+  for (int i = tid; i < nui - su; i += nt) U0e[i] = Ue[i + su];
+  for (int t = max(N - shift, 0); t < N; ++t)
+    for (int j = tid; j < m; j += nt) U0e[t * m + j] = Ue[(N - 1) * m + j];
 }
 
 // Debug / parity views of the structured path: rebuild the dense arrays the reference's LQ solver works with
