@@ -545,7 +545,10 @@ def run_native(args):
         if solver.lq_mode == _lib.LQ_SCAN:
             lq_name = "scan-parallel" if E <= 64 else "scan-serial"
         structured = bool(getattr(solver, "_structured", False)) and lq_name == "sequential"
-        lq_kernel = "lq3_kernel" if structured else {"sequential": "lq_seq_kernel", "scan-serial": "lq_scan_kernel"}.get(
+        # sequential, dense: the small-system kernel holds the whole horizon in shared memory (n, m <= 16, N <= 47 for SRBD,
+        # up to 6 waves of environments; csrc/mpxb.cu launch_lq_seq), the streaming kernel otherwise
+        seq_kernel = "lq_small_kernel" if (n <= 16 and m <= 16 and N <= 47 and E <= 6 * 148) else "lq_seq_kernel"
+        lq_kernel = "lq3_kernel" if structured else {"sequential": seq_kernel, "scan-serial": "lq_scan_kernel"}.get(
             lq_name, "pscan_init + pscan_combine x levels + pscan_gains + pscan_rollout")
         # DRAM traffic per launch of the two largest kernels from the newest ncu --set full capture of this command
         # (profiles/traffic.json names the capture); the run itself cannot read DRAM counters
