@@ -46,6 +46,9 @@ struct WbModel {
   uint16_t dir_off[WB_MAXDIR];
   uint8_t dir_b0[WB_MAXDIR], dir_nb[WB_MAXDIR];
   uint8_t item_dir[WB_MAXITEMS];
+  // FK shortcuts, exact: bit 0 = body_quat is the identity, bit 1 = jnt_pos is zero (true for most MJCF bodies; the
+  // products they save are multiplications by exact ones and zeros)
+  uint8_t body_flags[WB_MAXB];
 };
 
 // mpxb_model_desc (host, include/mpxb.h) -> WbModel: derived dof tables and contact ancestor masks
@@ -81,6 +84,8 @@ inline int wb_build_model(const mpxb_model_desc& d, WbModel* o) {
     for (int i = 0; i < 4; ++i) { w.body_quat[b][i] = d.body_quat[b][i]; w.iquat[b][i] = d.body_iquat[b][i]; }
     w.mass[b] = d.body_mass[b];
     w.qpos0[b] = d.jnt_qpos0[b];
+    w.body_flags[b] = uint8_t(((w.body_quat[b][0] == 1.f && w.body_quat[b][1] == 0.f && w.body_quat[b][2] == 0.f && w.body_quat[b][3] == 0.f) ? 1 : 0) |
+                              ((w.jnt_pos[b][0] == 0.f && w.jnt_pos[b][1] == 0.f && w.jnt_pos[b][2] == 0.f) ? 2 : 0));
     w.depth[b] = (b <= 1) ? 0 : w.depth[w.parent[b]] + 1;
     if (b > 1 && w.parent[b] < 1) return MPXB_EUNSUPPORTED;  // a single tree hanging off the floating base
     if (w.depth[b] + 1 > w.maxdepth) w.maxdepth = w.depth[b] + 1;

@@ -96,23 +96,34 @@ HD void wb_tree_fk(const WbModel& md, WbTree<NB, NV, NC, NI>& tr, const float* q
         }
       } else {
         float r[3], q2[4];
+        const unsigned fl = md.body_flags[b];   // bit 0: body_quat = identity, bit 1: jnt_pos = 0 (exact shortcuts)
         quat_rotate(quat, md.body_pos[b], r);
         for (int i = 0; i < 3; ++i) pos[i] = pos[i] + r[i];
-        quat_mul(quat, md.body_quat[b], q2);
-        for (int i = 0; i < 4; ++i) quat[i] = q2[i];
+        if (!(fl & 1u)) {
+          quat_mul(quat, md.body_quat[b], q2);
+          for (int i = 0; i < 4; ++i) quat[i] = q2[i];
+        }
         if (jt == WB_JNT_HINGE) {
           const int dj = md.dofadr[b];
           float anchor[3], axis[3], o[3], l[3], cdof[6], cd[6];
-          quat_rotate(quat, md.jnt_pos[b], r);
-          for (int i = 0; i < 3; ++i) anchor[i] = r[i] + pos[i];
+          if (fl & 2u) {
+            for (int i = 0; i < 3; ++i) anchor[i] = pos[i];
+          } else {
+            quat_rotate(quat, md.jnt_pos[b], r);
+            for (int i = 0; i < 3; ++i) anchor[i] = r[i] + pos[i];
+          }
           quat_rotate(quat, md.jnt_axis[b], axis);
           const float half = (qpos[dj + 1] - md.qpos0[b]) * 0.5f;
           const float sn = sinf(half), cs = cosf(half);
           const float qloc[4] = {cs, md.jnt_axis[b][0] * sn, md.jnt_axis[b][1] * sn, md.jnt_axis[b][2] * sn};
           quat_mul(quat, qloc, q2);
           for (int i = 0; i < 4; ++i) quat[i] = q2[i];
-          quat_rotate(quat, md.jnt_pos[b], r);
-          for (int i = 0; i < 3; ++i) { pos[i] = anchor[i] - r[i]; o[i] = ref[i] - anchor[i]; }
+          if (fl & 2u) {
+            for (int i = 0; i < 3; ++i) o[i] = ref[i] - anchor[i];   // pos stays at the anchor
+          } else {
+            quat_rotate(quat, md.jnt_pos[b], r);
+            for (int i = 0; i < 3; ++i) { pos[i] = anchor[i] - r[i]; o[i] = ref[i] - anchor[i]; }
+          }
           cross3(axis, o, l);
           for (int i = 0; i < 3; ++i) { cdof[i] = axis[i]; cdof[3 + i] = l[i]; }
           // rv = v_body + v_parent, the reference velocity of d qfrc_bias / d qvel
