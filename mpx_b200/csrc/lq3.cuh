@@ -79,6 +79,7 @@ struct Lq3Args {
   float *OK;         // [E][N+1][OKS]     p_t head | k_t
   float *dX, *dU, *dV, *slope;   // dense [E][N+1][n], [E][N][m], [E][N+1][n], [E]
   const int32_t* done;
+  int e0;            // first environment of a sliced launch (E is then the slice length; pointers address the whole batch)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(NT, lq3_min_blocks<Lq3Dims<NH, NTL, M, NCONE>>
   constexpr int NT1 = RB1 * CB;   // tiles of TP = P+ AB
   extern __shared__ __align__(128) float smem3[];
   float* const smem = smem3;
-  const int e = blockIdx.x, tid = threadIdx.x;
+  const int e = blockIdx.x + a.e0, tid = threadIdx.x;
   if (a.done && a.done[e]) return;
   const int N = a.N;
   // warp roles rotate with the CTA index (co-resident CTAs b, b + #SM, ... then keep their tile warps on different

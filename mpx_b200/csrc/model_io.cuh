@@ -15,6 +15,9 @@ struct ModelIO {
   size_t w_stride;  // floats between consecutive envs' W (0 = shared)
   const float *x0, *X, *U, *V;
   const int32_t* done;
+  // first environment of a sliced launch (the first-pass trial kernels and their reduction only: E is then the slice
+  // length; every pointer keeps addressing the whole batch)
+  int e0;
 };
 
 struct LinOut {
@@ -186,7 +189,7 @@ __global__ void trial_reduce_kernel(ModelIO io, TrialOut o, int n) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= io.E * o.nia || !trial_selected(o)) return;
-  const int e = warp / o.nia, ia = o.ia0 + warp - e * o.nia;
+  const int le = warp / o.nia, e = le + io.e0, ia = o.ia0 + warp - le * o.nia;
   if (io.done && io.done[e]) return;
   if (o.ia0 > 0 && o.need && !o.need[e]) return;
   const int N = io.N;

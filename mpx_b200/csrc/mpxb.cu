@@ -43,6 +43,10 @@ struct mpxb_model {
   Lq3Layout s3;
   WbModel wb_host;
   int device;
+  // LQ tail / line-search overlap (mpxb_mpc_step): a side stream and two events owned by the handle, SM count
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int sm_count;
 };
 
 // Entry points may be called with another device current (one handle per GPU, several GPUs per process): launch on
@@ -143,6 +147,13 @@ int dispatch_lq3(const Lq3Layout& s, const Lq3Args& a, cudaStream_t st) {
   return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA;
 }
 
+// resident CTAs per SM of the structured LQ kernel a layout dispatches to (shared-memory bound)
+int lq3_resident(const Lq3Layout& s) {
+  if (s.nh == 37 && s.m == 12) return lq3_min_blocks<Lq3Dims<37, 24, 12, 4>>();
+  if (s.nh == 51 && s.m == 19) return lq3_min_blocks<Lq3Dims<51, 24, 19, 0>>();
+  return 1;
+}
+
 int dispatch_lq_seq(int n, int m, const LqArgs& a, cudaStream_t st) {
   cudaError_t err;
 #define MPXB_LQ_CASE(NN, MM) if (n == NN && m == MM) { err = launch_lq_seq<NN, MM>(a, st); return err == cudaSuccess ? MPXB_OK : MPXB_ECUDA; }
@@ -201,6 +212,16 @@ int mpxb_model_create(const mpxb_model_desc* d, mpxb_model** out) {
     mdl->s3_ok = d->n > nh && lq3_supported(mdl->s3);
   }
   cudaGetDevice(&mdl->device);
+  mdl->side = nullptr; mdl->ev_fork = nullptr; mdl->ev_join = nullptr; mdl->sm_count = 148;
+  cudaDeviceGetAttribute(&mdl->sm_count, cudaDevAttrMultiProcessorCount, mdl->device);
+  if (d->kind != MPXB_KIND_SRBD) {
+    if (cudaStreamCreateWithFlags(&mdl->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&mdl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&mdl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      mpxb_model_destroy(mdl);
+      return MPXB_ECUDA;
+    }
+  }
   if (d->kind == MPXB_KIND_SRBD) {
     if (d->n != SRBD_N || d->m != SRBD_M || d->nref != SRBD_NREF || d->npar != SRBD_NPAR || d->nw != SRBD_NW) {
       delete mdl;
@@ -263,6 +284,9 @@ int mpxb_model_set_option(mpxb_model* m, int option, int value) {
 void mpxb_model_destroy(mpxb_model* m) {
   if (!m) return;
   if (m->wb_dev) cudaFree(m->wb_dev);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
 
@@ -282,6 +306,12 @@ static int dispatch_lq(int lq_mode, int n, int m, const LqArgs& la, float* scan_
   if (lq_mode == MPXB_LQ_SCAN_PARALLEL || (lq_mode == MPXB_LQ_SCAN && pscan_applies(la.E)))
     return dispatch_lq_pscan(n, m, la, scan_ws, st);
   return dispatch_lq_scan(n, m, la, scan_ws, st);
+}
+
+// MPXB_SPLIT_LQ=0 switches the LQ tail / line-search overlap off (measurement switch)
+static bool split_enabled() {
+  static const bool on = [] { const char* v = getenv("MPXB_SPLIT_LQ"); return !(v && v[0] == '0'); }();
+  return on;
 }
 
 static WsLayout layout_of(const mpxb_model* mdl, int E, int lq_mode) {
@@ -329,7 +359,7 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
     float* Xn = to_user ? X : ws + L.Xt;
     float* Un = to_user ? U : ws + L.Ut;
     float* Vn = to_user ? V : ws + L.Vt;
-    ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done};
+    ModelIO io{E, N, reference, parameter, W, w_env_stride, x0, Xc, Uc, Vc, done, 0};
     LinOut lo{ws + L.A, ws + L.B, ws + L.Q, ws + L.R, ws + L.M, ws + L.q, ws + L.r, ws + L.c, ws + L.cost,
               n, m, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
     if (structured) {
@@ -363,10 +393,26 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
               // whole-body models: the foot / GRF tail of the state never enters f, so those columns of A are zero
               d.kind == MPXB_KIND_SRBD ? 0 : 13 + 2 * d.n_joints};
     int rc;
+    // LQ tail / line-search overlap: one CTA per environment over `slots` resident CTAs leaves the last wave partly
+    // empty (Go2 x1024: 592 + 432).  The full waves (slice A) and the remainder (slice B) are launched separately, and
+    // the alpha = 1 trial points of slice A run on the handle's side stream while slice B's Riccati sweep is still
+    // going, filling the SMs the short wave leaves idle.  Same kernels on the same data: results are unchanged.
+    int EA = 0;
+    if (structured && !mdl->eager_line_search && mdl->side && split_enabled()) {
+      const int slots = mdl->sm_count * lq3_resident(s3);
+      const int rem = E % slots;
+      if (E > slots && rem > 0 && 10 * rem <= 9 * slots) EA = E - rem;
+    }
     if (structured) {
       Lq3Args l3{E, N, ws + L.ABc, ws + L.PK, ws + L.Kc, ws + L.Pc, ws + L.OKc, ws + L.dX, ws + L.dU, ws + L.dV,
-                 ws + L.slope, done};
-      rc = dispatch_lq3(s3, l3, st);
+                 ws + L.slope, done, 0};
+      if (EA > 0) {
+        l3.E = EA;
+        rc = dispatch_lq3(s3, l3, st);
+        if (rc == MPXB_OK && cudaEventRecord(mdl->ev_fork, st) != cudaSuccess) rc = MPXB_ECUDA;
+        l3.e0 = EA; l3.E = E - EA;
+      }
+      if (EA == 0 || rc == MPXB_OK) rc = dispatch_lq3(s3, l3, st);
     } else {
       rc = dispatch_lq(lq_mode, n, m, la, ws + L.scan, st);
     }
@@ -383,6 +429,19 @@ int mpxb_mpc_step(const mpxb_model* mdl, void* stream, int E, int lq_mode, int m
       if (mdl->eager_line_search) { to.ia0 = 0; to.nia = NALPHA; to.need = nullptr; to.need_count = nullptr; }
       else if (three) { to.ia0 = pass; to.nia = pass < 2 ? 1 : NALPHA - 2; to.update_need = (pass == 1); }
       else { to.ia0 = pass; to.nia = pass == 0 ? 1 : NALPHA - 1; }
+      if (pass == 0 && EA > 0) {
+        // slice A behind its own Riccati sweep on the side stream, slice B behind the whole sweep on `st`, then join
+        ModelIO ioA = io, ioB = io;
+        ioA.E = EA; ioA.e0 = 0; ioB.E = E - EA; ioB.e0 = EA;
+        if (cudaStreamWaitEvent(mdl->side, mdl->ev_fork, 0) != cudaSuccess) return MPXB_ECUDA;
+        rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, ioA, to, mdl->side);
+        if (rc != MPXB_OK) return rc;
+        if (cudaEventRecord(mdl->ev_join, mdl->side) != cudaSuccess) return MPXB_ECUDA;
+        rc = wb_launch_trial(mdl->wb_host, mdl->wb_dev, ioB, to, st);
+        if (rc != MPXB_OK) return rc;
+        if (cudaStreamWaitEvent(st, mdl->ev_join, 0) != cudaSuccess) return MPXB_ECUDA;
+        continue;
+      }
       if (d.kind == MPXB_KIND_SRBD) {
         const int wpb = 4;
         const int blocks = (E * to.nia + wpb - 1) / wpb;

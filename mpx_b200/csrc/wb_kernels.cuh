@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(NT, wb_trial_min_blocks<NB, NV, NC, NT>()) wb_
   };
   for (int item = blockIdx.x; item < nenv * per_env; item += gridDim.x) {
   const int le = item / per_env, rem = item - le * per_env;
-  const int e = listed ? o.need_count[1 + le] : le;
+  const int e = listed ? o.need_count[1 + le] : le + io.e0;
   const int ia = o.ia0 + rem / (N + 1), t = rem % (N + 1);
   if (io.done && io.done[e]) continue;
   if (o.ia0 > 0 && o.need && !o.need[e]) continue;  // accepted in an earlier pass: the smaller steps are never looked at
