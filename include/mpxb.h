@@ -17,8 +17,10 @@
  *   - return value: 0 on success, negative MPXB_E* for ARGUMENT errors only.  Numerical failure is reported
  *     in-band exactly like the reference (NaNs in the outputs, mpc_wrapper.py:96,280) plus status[e] != 0.
  *   - no global mutable state; a model handle is immutable after creation (options are set before the first
- *     step) and may be used from several streams of its device concurrently as long as each call has its own
- *     workspace.  A handle belongs to the device that was current at mpxb_model_create; every entry point
+ *     step) and may be used on several streams of its device as long as each call has its own workspace and the
+ *     calls on one handle are ISSUED from one host thread at a time: for batches above one wave of LQ CTAs
+ *     mpxb_mpc_step forks part of its line search onto a side stream owned by the handle (event fork / join on
+ *     `stream`, valid under stream capture), and those two events are per handle.  A handle belongs to the device that was current at mpxb_model_create; every entry point
  *     switches to that device for its launches and restores the caller's current device.
  *   - `workspace` must be 256-byte aligned.
  */
