@@ -16,6 +16,8 @@ import ctypes as C
 from functools import partial
 
 import numpy as np
+import os
+
 import torch
 
 from .. import _lib
@@ -179,7 +181,22 @@ class MpcSolver:
         # the parallel-in-time scan is elements + ceil(log2(N+1)) levels + gains + rollout; the other LQ kernels are one launch
         parallel_scan = self.lq_mode == _lib.LQ_SCAN_PARALLEL or (self.lq_mode == _lib.LQ_SCAN and self.n_env <= 64)
         lq = 3 + int(self.N).bit_length() if parallel_scan else 1
-        self.launches_per_call = (2 + lq + trial) * self.max_iter
+        self._launches_base = 2 + lq + trial
+
+    @property
+    def launches_per_call(self):
+        """Kernel launches of one solve().  Batches above one wave of LQ CTAs whose remainder leaves the last wave partly
+        empty run the structured LQ kernel and the first line-search pass as two slices each (csrc/mpxb.cu, `EA`):
+        one more LQ launch, one more trial kernel + reduction."""
+        extra = 0
+        if getattr(self, "_structured", False) and not self.eager_line_search and self.lq_mode == _lib.LQ_SEQUENTIAL \
+                and os.environ.get("MPXB_SPLIT_LQ", "1")[:1] != "0":
+            resident = {18: 4, 25: 2}.get(int(self.desc.nv), 1)
+            slots = _sm_count() * resident
+            rem = self.n_env % slots
+            if self.n_env > slots and rem > 0 and 10 * rem <= 9 * slots:
+                extra = 3
+        return (self._launches_base + extra) * self.max_iter
 
     def _set_structure(self, diagonal):
         self._structured = bool(diagonal)
